@@ -1,0 +1,105 @@
+/* TEST INFRASTRUCTURE ONLY — not product code.  See oracle_port.h.
+ *
+ * Algorithm-independent validator for (SA, LCP).  At the default (unbounded) context the
+ * reference's output is the unique suffix array under signed-char order with the shorter
+ * suffix first (src/Suffix_Array.cpp:71,76-77) and LCP[k] = lcp(SA[k-1], SA[k]), LCP[0] = 0
+ * — the predicate of the reference's own (never called) is_sorted(), :512-536.  The order
+ * is checked in O(n) through the inverse permutation instead of by character scans, so it
+ * is usable on highly repetitive texts; LCP is recomputed with Kasai's algorithm.
+ */
+#include "oracle_port.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+static inline uint64_t get_idx(const void* arr, int w, uint64_t k) {
+  return w == 4 ? (uint64_t)((const uint32_t*)arr)[k] : ((const uint64_t*)arr)[k];
+}
+
+int caps_check_sa_lcp(const char* text, uint64_t n, const void* sa, const void* lcp,
+                      int idx_bytes, uint64_t* bad_pos) {
+  if ((idx_bytes != 4 && idx_bytes != 8) || !text || !sa || !lcp) return 4;
+  if (n == 0) return 0;
+  const signed char* t = (const signed char*)text;
+  uint64_t* rank = malloc((n + 1) * sizeof(uint64_t)); /* rank+1, 0 = unseen / empty suffix */
+  if (!rank) return 4;
+  memset(rank, 0, (n + 1) * sizeof(uint64_t));
+  int rc = 0;
+  uint64_t bad = 0;
+
+  for (uint64_t k = 0; k < n; ++k) { /* permutation of [0, n) */
+    const uint64_t s = get_idx(sa, idx_bytes, k);
+    if (s >= n || rank[s] != 0) {
+      rc = 1, bad = k;
+      goto done;
+    }
+    rank[s] = k + 1;
+  }
+  rank[n] = 0; /* the empty suffix precedes everything */
+
+  for (uint64_t k = 1; k < n; ++k) { /* suffix a must precede suffix b */
+    const uint64_t a = get_idx(sa, idx_bytes, k - 1), b = get_idx(sa, idx_bytes, k);
+    if (t[a] > t[b] || (t[a] == t[b] && rank[a + 1] >= rank[b + 1])) {
+      rc = 2, bad = k;
+      goto done;
+    }
+  }
+
+  if (get_idx(lcp, idx_bytes, 0) != 0) {
+    rc = 3, bad = 0;
+    goto done;
+  }
+  { /* Kasai: walk the text, h drops by at most one per step */
+    uint64_t h = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      const uint64_t k = rank[i] - 1;
+      if (k == 0) {
+        h = 0;
+        continue;
+      }
+      const uint64_t j = get_idx(sa, idx_bytes, k - 1);
+      while (i + h < n && j + h < n && t[i + h] == t[j + h]) ++h;
+      if (get_idx(lcp, idx_bytes, k) != h) {
+        rc = 3;
+        if (bad == 0 || k < bad) bad = k;
+      }
+      if (rc) break;
+      if (h) --h;
+    }
+  }
+
+done:
+  if (rc && bad_pos) *bad_pos = bad;
+  free(rank);
+  return rc;
+}
+
+typedef struct {
+  const signed char* t;
+  uint64_t n;
+} naive_env;
+static naive_env g_env; /* qsort has no context argument; tiny inputs, single-threaded use */
+
+static int naive_cmp(const void* pa, const void* pb) {
+  const uint64_t a = *(const uint64_t*)pa, b = *(const uint64_t*)pb;
+  const uint64_t la = g_env.n - a, lb = g_env.n - b, m = la < lb ? la : lb;
+  for (uint64_t k = 0; k < m; ++k)
+    if (g_env.t[a + k] != g_env.t[b + k]) return g_env.t[a + k] < g_env.t[b + k] ? -1 : 1;
+  return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+
+int caps_naive_sa_lcp(const char* text, uint64_t n, uint64_t* sa_out, uint64_t* lcp_out) {
+  g_env.t = (const signed char*)text;
+  g_env.n = n;
+  for (uint64_t i = 0; i < n; ++i) sa_out[i] = i;
+  qsort(sa_out, n, sizeof(uint64_t), naive_cmp);
+  for (uint64_t k = 0; k < n; ++k) {
+    uint64_t h = 0;
+    if (k) {
+      const uint64_t a = sa_out[k - 1], b = sa_out[k];
+      while (a + h < n && b + h < n && g_env.t[a + h] == g_env.t[b + h]) ++h;
+    }
+    lcp_out[k] = h;
+  }
+  return 0;
+}
