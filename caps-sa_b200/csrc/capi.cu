@@ -1,0 +1,262 @@
+// C-ABI layer (include/caps_sa_gpu.h): argument checks, host<->device staging, and the
+// translation of capsb::Error into return codes.  No CPU fallback anywhere: without a CUDA
+// device every entry point fails loudly.
+#include <cstring>
+#include <new>
+
+#include "../../include/caps_sa_gpu.h"
+#include "engine.cuh"
+
+using capsb::Engine;
+
+struct caps_sa_gpu_engine {
+  Engine impl;
+  explicit caps_sa_gpu_engine(int device) : impl(device) {}
+};
+
+namespace {
+
+thread_local std::string g_last_error;
+
+template <class F>
+int guarded(F&& body) {
+  try {
+    g_last_error.clear();
+    return body();
+  } catch (const capsb::Error& e) {
+    g_last_error = e.what();
+    // leave the device usable for the next call if the error was recoverable
+    cudaGetLastError();
+    return CAPS_SA_GPU_ERR_CUDA;
+  } catch (const std::bad_alloc&) {
+    g_last_error = "host allocation failed";
+    return CAPS_SA_GPU_ERR_CUDA;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return CAPS_SA_GPU_ERR_CUDA;
+  }
+}
+
+int bad_args(const char* why) {
+  g_last_error = why;
+  return CAPS_SA_GPU_ERR_ARGS;
+}
+
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() {
+    CAPSB_CUDA(cudaEventCreate(&a));
+    CAPSB_CUDA(cudaEventCreate(&b));
+  }
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+  float ms() {
+    float v = 0;
+    CAPSB_CUDA(cudaEventElapsedTime(&v, a, b));
+    return v;
+  }
+};
+
+template <class IdxT>
+int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, IdxT* sa_out, IdxT* lcp_out,
+                   uint64_t max_context) {
+  if (!engine) return bad_args("engine is NULL");
+  if (n > 0 && (!text || !sa_out || !lcp_out)) return bad_args("NULL buffer");
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
+  if (max_context != 0 && max_context < n) {
+    g_last_error = "bounded context (max_context < n) is not supported by the GPU engine";
+    return CAPS_SA_GPU_ERR_UNSUPPORTED;
+  }
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    cudaStream_t st = eng.stream;
+    capsb::DevBuf<uint8_t> d_text(n, st);
+    capsb::DevBuf<IdxT> d_sa(n, st), d_lcp(n, st);
+    EventPair h2d, d2h;
+    CAPSB_CUDA(cudaEventRecord(h2d.a, st));
+    CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
+    CAPSB_CUDA(cudaEventRecord(h2d.b, st));
+    capsb::build_sa_lcp<IdxT>(eng, d_text.get(), n, d_sa.get(), d_lcp.get());
+    CAPSB_CUDA(cudaEventRecord(d2h.a, st));
+    CAPSB_CUDA(cudaMemcpyAsync(sa_out, d_sa.get(), n * sizeof(IdxT), cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaMemcpyAsync(lcp_out, d_lcp.get(), n * sizeof(IdxT), cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaEventRecord(d2h.b, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    eng.stats.ms_h2d = h2d.ms();
+    eng.stats.ms_d2h = d2h.ms();
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+template <class IdxT>
+int construct_device(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, IdxT* d_sa, IdxT* d_lcp,
+                     void* stream) {
+  if (!engine) return bad_args("engine is NULL");
+  if (n > 0 && (!d_text || !d_sa || !d_lcp)) return bad_args("NULL buffer");
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    capsb::StreamScope scope(eng, stream ? static_cast<cudaStream_t>(stream) : eng.stream);
+    capsb::build_sa_lcp<IdxT>(eng, static_cast<const uint8_t*>(d_text), n, d_sa, d_lcp);
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+}  // namespace
+
+extern "C" {
+
+int caps_sa_gpu_device_count(void) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return count;
+}
+
+const char* caps_sa_gpu_last_error(void) { return g_last_error.c_str(); }
+
+caps_sa_gpu_engine* caps_sa_gpu_engine_create(int device) {
+  caps_sa_gpu_engine* out = nullptr;
+  const int rc = guarded([&]() -> int {
+    int count = 0;
+    CAPSB_CUDA(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count)
+      capsb::fail("no such CUDA device: " + std::to_string(device) + " (visible: " + std::to_string(count) + ")");
+    out = new caps_sa_gpu_engine(device);
+    return CAPS_SA_GPU_OK;
+  });
+  return rc == CAPS_SA_GPU_OK ? out : nullptr;
+}
+
+void caps_sa_gpu_engine_destroy(caps_sa_gpu_engine* engine) { delete engine; }
+
+int caps_sa_gpu_engine_stats(const caps_sa_gpu_engine* engine, caps_sa_gpu_stats* out) {
+  if (!engine || !out) return bad_args("NULL argument");
+  const capsb::Stats& s = engine->impl.stats;
+  out->n = s.n;
+  out->idx_bytes = s.idx_bytes;
+  out->bits_per_symbol = s.bits_per_symbol;
+  out->alphabet_size = s.alphabet_size;
+  out->refine_rounds = s.refine_rounds;
+  out->tied_after_key_sort = s.tied_after_key_sort;
+  out->deep_lcp_direct = s.deep_lcp_direct;
+  out->deep_lcp_long = s.deep_lcp_long;
+  out->kernel_launches = s.kernel_launches;
+  out->ms_pack = s.ms_pack, out->ms_sort = s.ms_sort, out->ms_heads = s.ms_heads;
+  out->ms_refine = s.ms_refine, out->ms_deep_lcp = s.ms_deep_lcp, out->ms_total = s.ms_total;
+  out->ms_h2d = s.ms_h2d, out->ms_d2h = s.ms_d2h;
+  return CAPS_SA_GPU_OK;
+}
+
+int caps_sa_gpu_construct_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n, uint32_t* sa_out,
+                              uint32_t* lcp_out, uint64_t /*subproblem_count*/, uint64_t max_context) {
+  return construct_host<uint32_t>(engine, text, n, sa_out, lcp_out, max_context);
+}
+int caps_sa_gpu_construct_u64(caps_sa_gpu_engine* engine, const char* text, uint64_t n, uint64_t* sa_out,
+                              uint64_t* lcp_out, uint64_t /*subproblem_count*/, uint64_t max_context) {
+  return construct_host<uint64_t>(engine, text, n, sa_out, lcp_out, max_context);
+}
+int caps_sa_gpu_construct_device_u32(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, uint32_t* d_sa,
+                                     uint32_t* d_lcp, void* stream) {
+  return construct_device<uint32_t>(engine, d_text, n, d_sa, d_lcp, stream);
+}
+int caps_sa_gpu_construct_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, uint64_t* d_sa,
+                                     uint64_t* d_lcp, void* stream) {
+  return construct_device<uint64_t>(engine, d_text, n, d_sa, d_lcp, stream);
+}
+
+int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n) {
+  if (!engine) return bad_args("engine is NULL");
+  if (n > 0 && !text) return bad_args("NULL buffer");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    capsb::DevBuf<uint8_t> d(n, eng.stream);
+    CAPSB_CUDA(cudaMemcpyAsync(d.get(), text, n, cudaMemcpyHostToDevice, eng.stream));
+    capsb::map_acgt_device(eng, d.get(), n);
+    CAPSB_CUDA(cudaMemcpyAsync(text, d.get(), n, cudaMemcpyDeviceToHost, eng.stream));
+    CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+void* caps_sa_gpu_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+    cudaGetLastError();
+    g_last_error = "cudaHostAlloc failed";
+    return nullptr;
+  }
+  return p;
+}
+void caps_sa_gpu_host_free(void* ptr) {
+  if (ptr) cudaFreeHost(ptr);
+}
+
+int caps_sa_gpu_stage_pack(caps_sa_gpu_engine* engine, const char* text, uint64_t n, uint64_t* words_out,
+                           uint64_t* nwords_out, uint32_t* alphabet_size_out) {
+  if (!engine || !text || !words_out || !nwords_out) return -bad_args("NULL argument");
+  int bits = 0;
+  const int rc = guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    capsb::DevBuf<uint8_t> d(n ? n : 1, eng.stream);
+    CAPSB_CUDA(cudaMemcpyAsync(d.get(), text, n, cudaMemcpyHostToDevice, eng.stream));
+    capsb::PackedTextBuf p = capsb::pack_text(eng, d.get(), n);
+    CAPSB_CUDA(cudaMemcpyAsync(words_out, p.words.get(), p.nwords * sizeof(uint64_t), cudaMemcpyDeviceToHost,
+                               eng.stream));
+    CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+    *nwords_out = p.nwords;
+    if (alphabet_size_out) *alphabet_size_out = p.sigma;
+    bits = 1 << p.log2_bits;
+    return CAPS_SA_GPU_OK;
+  });
+  return rc == CAPS_SA_GPU_OK ? bits : -rc;
+}
+
+int caps_sa_gpu_stage_radix_sort_u64_u32(caps_sa_gpu_engine* engine, uint64_t* keys, uint32_t* vals, uint64_t n,
+                                         unsigned begin_bit, unsigned end_bit) {
+  if (!engine || (n && (!keys || !vals))) return bad_args("NULL argument");
+  if (end_bit > 64 || begin_bit >= end_bit) return bad_args("bad bit range");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    cudaStream_t st = eng.stream;
+    capsb::DevBuf<uint64_t> ka(n, st), kb(n, st);
+    capsb::DevBuf<uint32_t> va(n, st), vb(n, st);
+    CAPSB_CUDA(cudaMemcpyAsync(ka.get(), keys, n * 8, cudaMemcpyHostToDevice, st));
+    CAPSB_CUDA(cudaMemcpyAsync(va.get(), vals, n * 4, cudaMemcpyHostToDevice, st));
+    const int where = capsb::radix_sort_pairs<uint64_t, uint32_t>(st, eng.radix, ka.get(), va.get(), kb.get(),
+                                                                  vb.get(), n, begin_bit, end_bit);
+    CAPSB_CUDA(cudaMemcpyAsync(keys, where ? kb.get() : ka.get(), n * 8, cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaMemcpyAsync(vals, where ? vb.get() : va.get(), n * 4, cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+int caps_sa_gpu_stage_scan_u32(caps_sa_gpu_engine* engine, uint32_t* data, uint64_t n, int inclusive_max) {
+  if (!engine || (n && !data)) return bad_args("NULL argument");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    cudaStream_t st = eng.stream;
+    capsb::DevBuf<uint32_t> in(n, st), out(n, st);
+    CAPSB_CUDA(cudaMemcpyAsync(in.get(), data, n * 4, cudaMemcpyHostToDevice, st));
+    capsb::stage_scan_u32(eng, in.get(), out.get(), n, inclusive_max != 0);
+    CAPSB_CUDA(cudaMemcpyAsync(data, out.get(), n * 4, cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,79 @@
+// Engine: per-device context (stream, scratch, statistics) and the stage entry points.
+#pragma once
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "packed_text.cuh"
+#include "radix_sort.cuh"
+
+namespace capsb {
+
+// Per-construction statistics, mirrored by caps_sa_gpu_stats in include/caps_sa_gpu.h.
+struct Stats {
+  uint64_t n = 0;
+  uint32_t idx_bytes = 0;
+  uint32_t bits_per_symbol = 0;
+  uint32_t alphabet_size = 0;
+  uint32_t refine_rounds = 0;
+  uint64_t tied_after_key_sort = 0;  // suffixes whose 64-bit key equals their predecessor's
+  uint64_t deep_lcp_direct = 0;      // irreducible deep LCPs computed by comparison
+  uint64_t deep_lcp_long = 0;        // ... of which needed the block-wide compare
+  uint64_t kernel_launches = 0;
+  float ms_pack = 0, ms_sort = 0, ms_heads = 0, ms_refine = 0, ms_deep_lcp = 0, ms_total = 0;
+  float ms_h2d = 0, ms_d2h = 0;
+};
+
+struct PackedTextBuf {
+  DevBuf<uint64_t> words;
+  uint64_t nwords = 0;
+  unsigned log2_bits = 3;
+  unsigned sigma = 0;
+  PackedText view(uint64_t n) const { return PackedText{words.get(), n, log2_bits}; }
+};
+
+struct Engine {
+  DeviceInfo dev;
+  cudaStream_t stream = nullptr;
+  bool owns_stream = false;
+  RadixScratch radix;
+  ScanScratch<uint32_t> scan32;
+  ScanScratch<uint64_t> scan64;
+  Stats stats;
+  std::vector<cudaEvent_t> events;
+
+  explicit Engine(int device);
+  ~Engine();
+  Engine(const Engine&) = delete;
+  Engine& operator=(const Engine&) = delete;
+
+  template <class T>
+  ScanScratch<T>& scan_scratch();
+};
+
+template <>
+inline ScanScratch<uint32_t>& Engine::scan_scratch<uint32_t>() { return scan32; }
+template <>
+inline ScanScratch<uint64_t>& Engine::scan_scratch<uint64_t>() { return scan64; }
+
+// Temporarily run an engine on a caller-provided stream.
+struct StreamScope {
+  Engine& eng;
+  cudaStream_t saved;
+  StreamScope(Engine& e, cudaStream_t s) : eng(e), saved(e.stream) { eng.stream = s; }
+  ~StreamScope() { eng.stream = saved; }
+};
+
+// text_pack.cu
+PackedTextBuf pack_text(Engine& eng, const uint8_t* d_text, uint64_t n);
+void map_acgt_device(Engine& eng, uint8_t* d_text, uint64_t n);
+
+// sa_build.cu — the construction path (reference construct(), src/Suffix_Array.cpp:466-494)
+template <class IdxT>
+void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, IdxT* d_lcp);
+
+// Test hook: the two scan flavours the pipeline uses (inclusive max, exclusive sum).
+void stage_scan_u32(Engine& eng, const uint32_t* d_in, uint32_t* d_out, uint64_t n, bool inclusive_max);
+
+}  // namespace capsb

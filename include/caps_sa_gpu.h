@@ -1,0 +1,115 @@
+/* caps_sa_gpu.h — C-ABI of the B200-native CaPS-SA construction engine.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch
+ * types.  The C++ class shell in include/Suffix_Array.hpp (same public surface as the
+ * reference's CaPS_SA::Suffix_Array<idx_t>, reference include/Suffix_Array.hpp:22-181) and
+ * the Python mirror in caps-sa_b200/ bind exactly these entry points.  There is no CPU
+ * fallback: every function fails (non-zero return + caps_sa_gpu_last_error()) when no CUDA
+ * device / kernel image is available.
+ *
+ * Semantics (identical to the reference at its default, unbounded context):
+ *   SA  = suffix array of text[0..n) under `signed char` order (reference
+ *         src/Suffix_Array.cpp:77,289), the shorter suffix first when one is a prefix of
+ *         the other (:71,76);
+ *   LCP[0] = 0, LCP[k] = lcp(text[SA[k-1]..], text[SA[k]..]).
+ * Results do not depend on subproblem_count (a tuning hint here, as in the reference the
+ * output is independent of p — SURVEY.md §0).
+ */
+#ifndef CAPS_SA_GPU_H
+#define CAPS_SA_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPS_SA_GPU_OK 0
+#define CAPS_SA_GPU_ERR_ARGS 1     /* bad arguments (NULL pointers, n too large for the index width) */
+#define CAPS_SA_GPU_ERR_CUDA 2     /* CUDA / NCCL failure, including out of device memory */
+#define CAPS_SA_GPU_ERR_UNSUPPORTED 3 /* e.g. bounded context */
+
+/* Opaque per-device engine: stream, scratch pools, statistics. */
+typedef struct caps_sa_gpu_engine caps_sa_gpu_engine;
+
+/* Statistics of the last construction on an engine (times in ms, CUDA events on the
+ * engine's stream). */
+typedef struct caps_sa_gpu_stats {
+  uint64_t n;
+  uint32_t idx_bytes;
+  uint32_t bits_per_symbol;     /* 1, 2, 4 or 8: width of the packed codes */
+  uint32_t alphabet_size;
+  uint32_t refine_rounds;       /* prefix-doubling rounds run on the tied suffixes */
+  uint64_t tied_after_key_sort; /* suffixes whose 64-bit key equals their predecessor's */
+  uint64_t deep_lcp_direct;     /* irreducible deep LCPs computed by direct comparison */
+  uint64_t deep_lcp_long;       /* ... that needed the block-wide comparison */
+  uint64_t kernel_launches;     /* launches of this library's kernels */
+  float ms_pack, ms_sort, ms_heads, ms_refine, ms_deep_lcp, ms_total;
+  float ms_h2d, ms_d2h;         /* host-buffer entry points only */
+} caps_sa_gpu_stats;
+
+/* Number of CUDA devices visible to the library (0 if none / driver missing). */
+int caps_sa_gpu_device_count(void);
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* caps_sa_gpu_last_error(void);
+
+/* Engine lifetime.  caps_sa_gpu_engine_create returns NULL on failure. */
+caps_sa_gpu_engine* caps_sa_gpu_engine_create(int device);
+void caps_sa_gpu_engine_destroy(caps_sa_gpu_engine* engine);
+int caps_sa_gpu_engine_stats(const caps_sa_gpu_engine* engine, caps_sa_gpu_stats* out);
+
+/* ---- Host-buffer construction: what Suffix_Array<idx_t>::construct() binds --------------
+ * Replaces the reference's construct() (src/Suffix_Array.cpp:466-494).  `text` is borrowed
+ * host memory of n bytes; sa_out / lcp_out are caller-owned host arrays of n entries
+ * (pinned memory from caps_sa_gpu_host_alloc makes the copies run at PCIe speed).
+ * Blocking.  max_context: 0 or >= n only (the reference's default); otherwise
+ * CAPS_SA_GPU_ERR_UNSUPPORTED.  num_gpus: 0 or 1 = one device (the engine's). */
+int caps_sa_gpu_construct_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
+                              uint32_t* sa_out, uint32_t* lcp_out, uint64_t subproblem_count,
+                              uint64_t max_context);
+int caps_sa_gpu_construct_u64(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
+                              uint64_t* sa_out, uint64_t* lcp_out, uint64_t subproblem_count,
+                              uint64_t max_context);
+
+/* ---- Device-resident construction --------------------------------------------------------
+ * d_text (n bytes), d_sa, d_lcp (n entries each) are device pointers on the engine's
+ * device; `stream` is a cudaStream_t (NULL = the engine's own stream).  The call returns
+ * after the work has completed on that stream (it contains small device-to-host reads). */
+int caps_sa_gpu_construct_device_u32(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
+                                     uint32_t* d_sa, uint32_t* d_lcp, void* stream);
+int caps_sa_gpu_construct_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
+                                     uint64_t* d_sa, uint64_t* d_lcp, void* stream);
+
+/* ---- CLI byte mapping ----------------------------------------------------------------------
+ * In-place text[i] = "ACTG"[(toupper(text[i]) & 6) >> 1] for every byte, run on the device
+ * (reference src/main.cpp:61-70).  `text` is host memory. */
+int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n);
+
+/* ---- Pinned host memory ---------------------------------------------------------------------
+ * The class shell allocates SA_/LCP_ with these (reference: malloc in the ctor,
+ * src/Suffix_Array.cpp:20-21, include/Suffix_Array.hpp:137-142). */
+void* caps_sa_gpu_host_alloc(size_t bytes);
+void caps_sa_gpu_host_free(void* ptr);
+
+/* ---- Stage-level entry points (parity tests of the individual kernels) ----------------------
+ * All operate on host arrays and run the production kernels on the engine's device. */
+
+/* Packs `text` and returns bits per symbol (1/2/4/8) or a negative error; words_out must
+ * hold ceil(n*8/64)+2 entries (enough for any width); *nwords_out receives the count. */
+int caps_sa_gpu_stage_pack(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
+                           uint64_t* words_out, uint64_t* nwords_out, uint32_t* alphabet_size_out);
+
+/* Stable LSD radix sort of (keys, vals) on key bits [begin_bit, end_bit), in place. */
+int caps_sa_gpu_stage_radix_sort_u64_u32(caps_sa_gpu_engine* engine, uint64_t* keys, uint32_t* vals,
+                                         uint64_t n, unsigned begin_bit, unsigned end_bit);
+
+/* Inclusive max-scan and exclusive sum-scan of a uint32 array (the two scan flavours the
+ * pipeline uses), in place. */
+int caps_sa_gpu_stage_scan_u32(caps_sa_gpu_engine* engine, uint32_t* data, uint64_t n, int inclusive_max);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPS_SA_GPU_H */

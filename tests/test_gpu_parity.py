@@ -1,0 +1,228 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C-ABI,
+against the oracle — committed reference fixtures, the plain-C restatement / the compiled
+unmodified reference on seeded inputs, and the independent checker at larger sizes."""
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import GOLDEN_DIR, ROOT, golden_cases, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(pkg):
+    eng = pkg.Engine(0)
+    yield eng
+    eng.close()
+
+
+def gpu_sa_lcp(pkg, engine, text, idx_bytes=4):
+    sa = pkg.SuffixArray(text, idx_bytes=idx_bytes, engine=engine)
+    sa.construct()
+    return sa.SA().copy(), sa.LCP().copy(), sa.stats()
+
+
+# ---- stage-level parity -----------------------------------------------------------------
+def numpy_pack(text):
+    present = np.zeros(256, dtype=bool)
+    present[np.unique(text)] = True
+    order = [(k + 128) & 255 for k in range(256)]  # signed-char order
+    lut = np.zeros(256, dtype=np.uint64)
+    code = 0
+    for b in order:
+        if present[b]:
+            lut[b] = code
+            code += 1
+    sigma = code
+    log2_bits = 0
+    while (1 << (1 << log2_bits)) < sigma:
+        log2_bits += 1
+    bits = 1 << log2_bits
+    per = 64 // bits
+    nwords = -(-len(text) * bits // 64) + 2
+    codes = np.zeros(nwords * per, dtype=np.uint64)
+    codes[:len(text)] = lut[text]
+    codes = codes.reshape(nwords, per)
+    shifts = np.uint64(64 - bits) - np.arange(per, dtype=np.uint64) * np.uint64(bits)
+    words = np.bitwise_or.reduce(codes << shifts, axis=1)
+    return bits, words, sigma
+
+
+@pytest.mark.parametrize("maker", [
+    lambda s: s.random_acgt(100_003, 1),
+    lambda s: s.random_bytes(50_001, 2),
+    lambda s: s.random_bytes(70_000, 3, sigma=2, base=0x7F),
+    lambda s: s.random_bytes(33_333, 4, sigma=11, base=0xFA),
+    lambda s: np.full(1000, ord("A"), dtype=np.uint8),
+    lambda s: s.random_acgt(17, 5),
+])
+def test_stage_pack(engine, synth, maker):
+    text = maker(synth)
+    bits, words, sigma = engine.stage_pack(text)
+    wbits, wwords, wsigma = numpy_pack(text)
+    assert (bits, sigma) == (wbits, wsigma)
+    assert np.array_equal(words, wwords)
+
+
+@pytest.mark.parametrize("n", [1, 31, 4096, 4097, 100_000, 3_000_001])
+def test_stage_radix_sort_is_a_stable_sort(engine, n):
+    rng = np.random.default_rng(n)
+    keys = rng.integers(0, 1 << 63, size=n, dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=n, dtype=np.uint64)
+    keys[rng.integers(0, n, size=n // 3)] = keys[0]  # plenty of duplicates
+    vals = np.arange(n, dtype=np.uint32)
+    gk, gv = engine.stage_radix_sort(keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(gk, keys[order])
+    assert np.array_equal(gv, vals[order])
+
+
+def test_stage_radix_sort_bit_range(engine):
+    rng = np.random.default_rng(7)
+    n = 200_000
+    keys = rng.integers(0, 1 << 40, size=n, dtype=np.uint64)
+    vals = np.arange(n, dtype=np.uint32)
+    gk, gv = engine.stage_radix_sort(keys, vals, 8, 24)
+    order = np.argsort((keys >> np.uint64(8)) & np.uint64(0xFFFF), kind="stable")
+    assert np.array_equal(gv, vals[order])
+    assert np.array_equal(gk, keys[order])
+
+
+@pytest.mark.parametrize("n", [1, 255, 2048, 2049, 1_000_003])
+def test_stage_scans(engine, n):
+    rng = np.random.default_rng(n)
+    data = rng.integers(0, 5, size=n, dtype=np.uint32)
+    got = engine.stage_scan(data, inclusive_max=False)
+    want = np.concatenate([[0], np.cumsum(data[:-1], dtype=np.uint64)]).astype(np.uint32)
+    assert np.array_equal(got, want)
+    marks = np.where(rng.random(n) < 0.01, np.arange(n), 0).astype(np.uint32)
+    got = engine.stage_scan(marks, inclusive_max=True)
+    assert np.array_equal(got, np.maximum.accumulate(marks))
+
+
+# ---- whole-path parity: committed reference fixtures ------------------------------------------
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_fixture(pkg, engine, name):
+    g = load_golden(name)
+    sa, lcp, _ = gpu_sa_lcp(pkg, engine, g["text"], g["idx_bytes"])
+    assert np.array_equal(sa, g["sa"]), "SA differs from the reference fixture"
+    assert np.array_equal(lcp, g["lcp"]), "LCP differs from the reference fixture"
+
+
+def test_golden_dump_digest_simpletest2(pkg, engine, tmp_path):
+    g = load_golden("simpletest2_cli")
+    obj = pkg.SuffixArray(g["text"], engine=engine)
+    obj.construct()
+    path = tmp_path / "dump.bin"
+    obj.dump(path)
+    digest = hashlib.sha256(path.read_bytes()).hexdigest()
+    assert digest == "36c1179e82ddbc8d8c7dc2af9c164ea7e6326b22116fe9f2347d2d4488621713"
+
+
+# ---- whole-path parity: oracle on seeded inputs ---------------------------------------------------
+def oracle_sa_lcp(text, p, idx_bytes=4):
+    if oracle_lib.ref() is not None:
+        sa, lcp, _ = oracle_lib.ref_sa_lcp(text, subproblems=p, idx_bytes=idx_bytes)
+        return sa, lcp
+    return oracle_lib.port_sa_lcp(text, subproblems=p, idx_bytes=idx_bytes)
+
+
+CASES = {
+    "acgt_1M": lambda s: (s.random_acgt(1_000_000, 101), 64),
+    "acgt_odd_777777": lambda s: (s.random_acgt(777_777, 102), 32),
+    "genome_like_2M": lambda s: (s.genome_like(2_000_000, seed=103, scale=0.004), 64),
+    "bytes256_500k": lambda s: (s.random_bytes(500_000, 104), 32),
+    "sigma12_400k": lambda s: (s.random_bytes(400_000, 105, sigma=12, base=0x79), 32),
+    "sigma2_600k": lambda s: (s.random_bytes(600_000, 106, sigma=2, base=0xFF), 32),
+    "periodic_unit1000_300k": lambda s: (s.periodic_random_unit(300_000, 1000, seed=4), 16),
+    "period3_200k": lambda s: (s.periodic(200_000, b"ACG"), 16),
+    "fibonacci_400k": lambda s: (s.fibonacci(400_000), 16),
+    "allA_100k": lambda s: (np.full(100_000, ord("A"), dtype=np.uint8), 8),
+    "ecoli_like_cli_mapped": lambda s: (s.map_acgt(s.ecoli_like_fasta(seed=1, bases=1_000_000)), 64),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_matches_oracle(pkg, engine, synth, case):
+    text, p = CASES[case](synth)
+    want_sa, want_lcp = oracle_sa_lcp(text, p)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
+    assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
+
+
+@pytest.mark.parametrize("case", ["acgt_1M", "genome_like_2M", "fibonacci_400k", "bytes256_500k"])
+def test_u64_indices_match_oracle(pkg, engine, synth, case):
+    text, p = CASES[case](synth)
+    text = text[:300_000]
+    want_sa, want_lcp = oracle_sa_lcp(text, 16, idx_bytes=8)
+    sa, lcp, _ = gpu_sa_lcp(pkg, engine, text, idx_bytes=8)
+    assert sa.dtype == np.uint64
+    assert np.array_equal(sa, want_sa) and np.array_equal(lcp, want_lcp)
+
+
+def test_tiny_inputs_below_reference_minimum(pkg, engine):
+    # the reference cannot run n < 16 (SIGFPE); the engine must still be correct there
+    for raw in (b"A", b"AC", b"banana\n", b"mississippi", b"AAAAAAAAAAAAAAA"):
+        text = np.frombuffer(raw, dtype=np.uint8)
+        sa, lcp, _ = gpu_sa_lcp(pkg, engine, text)
+        nsa, nlcp = oracle_lib.naive_sa_lcp(text)
+        assert np.array_equal(sa, nsa.astype(np.uint32)) and np.array_equal(lcp, nlcp.astype(np.uint32)), raw
+
+
+# ---- larger sizes: golden digest + independent checker ------------------------------------------
+def test_golden_digest_16M_random(pkg, engine, synth):
+    with open(os.path.join(GOLDEN_DIR, "golden_hashes.json")) as f:
+        gold = json.load(f)
+    text = synth.random_acgt(16_000_000, 2)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    digest = hashlib.sha256(oracle_lib.dump_bytes(len(text), sa, lcp)).hexdigest()
+    assert digest == gold["large"]["acgt_seed2_16M"]["dump_sha256"] == gold["survey_appendix_A"]["acgt_seed2_16M_dump_sha256"]
+
+
+def test_checker_periodic_20M_bytes(pkg, engine, synth):
+    text = synth.periodic_random_unit(20_000_000, 1000, seed=4)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    assert oracle_lib.check_sa_lcp(text, sa, lcp) == (0, 0), stats
+    assert int(lcp.max()) == len(text) - 1000
+
+
+def test_checker_genome_like_50M(pkg, engine, synth):
+    text = synth.genome_like(50_000_000, seed=3)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    assert oracle_lib.check_sa_lcp(text, sa, lcp) == (0, 0), stats
+
+
+# ---- CLI: same file in, same file out ----------------------------------------------------------------
+def test_cli_dump_matches_reference_cli(pkg, synth, tmp_path):
+    raw = synth.ecoli_like_fasta(seed=1, bases=400_000)
+    src = tmp_path / "ecoli_like.fa"
+    raw.tofile(src)
+    out_gpu = tmp_path / "gpu.bin"
+    proc = subprocess.run([os.path.join(ROOT, "bin", "caps_sa"), str(src), str(out_gpu), "64"],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    assert f"Text length: {len(raw)}." in proc.stderr
+    assert "Constructed the suffix array. Time taken:" in proc.stderr
+    assert "Dumped the suffix array. Time taken:" in proc.stderr
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "caps_sa_ref")
+    if os.path.exists(ref_cli):
+        out_cpu = tmp_path / "cpu.bin"
+        subprocess.run([ref_cli, str(src), str(out_cpu), "64"], check=True, capture_output=True)
+        assert out_gpu.read_bytes() == out_cpu.read_bytes()
+    else:
+        mapped = synth.map_acgt(raw)
+        sa, lcp = oracle_lib.port_sa_lcp(mapped, subproblems=64)
+        assert out_gpu.read_bytes() == oracle_lib.dump_bytes(len(mapped), sa, lcp)
+
+
+def test_map_acgt_kernel(engine, synth):
+    raw = np.concatenate([np.arange(256, dtype=np.uint8).repeat(5), synth.random_bytes(100_001, 9)])
+    got = raw.copy()
+    engine.map_acgt(got)
+    assert np.array_equal(got, synth.map_acgt(raw))
