@@ -175,6 +175,26 @@ __global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const uint
   }
 }
 
+// LCP of neighbours with different keys comes from the keys alone: clz(key_a ^ key_b) / bits,
+// bounded by the shorter suffix.  It needs the FINAL predecessor (the bound depends on which
+// member of the previous group ends up last), so it runs after the refinement.
+template <class IdxT>
+void key_lcp(Engine& eng, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp, uint64_t n, unsigned log2_bits) {
+  launch_map(eng.dev, eng.stream, n, [=] __device__(uint64_t k) {
+    if (k == 0) {
+      d_lcp[0] = 0;
+      return;
+    }
+    const uint64_t x = keys[k] ^ keys[k - 1];
+    if (x != 0) {
+      const uint64_t a = d_sa[k - 1], b = d_sa[k];
+      const uint64_t shorter = n - (a > b ? a : b);
+      const uint64_t l = static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> log2_bits;
+      d_lcp[k] = static_cast<IdxT>(l < shorter ? l : shorter);
+    }
+  });
+}
+
 }  // namespace
 
 template <class IdxT>
@@ -225,26 +245,14 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   const uint64_t* keys = key_b.get();
   clock.mark();  // 2
 
-  // ---- 3. LCP of neighbours with different keys; count the ties --------------------------
-  launch_map(dev, st, n, [=] __device__(uint64_t k) {
-    if (k == 0) {
-      d_lcp[0] = 0;
-      return;
-    }
-    const uint64_t x = keys[k] ^ keys[k - 1];
-    if (x != 0) {
-      const uint64_t a = d_sa[k - 1], b = d_sa[k];
-      const uint64_t shorter = n - (a > b ? a : b);
-      const uint64_t l = static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> log2_bits;
-      d_lcp[k] = static_cast<IdxT>(l < shorter ? l : shorter);
-    }
-  });
+  // ---- 3. count the suffixes whose key ties with their predecessor --------------------------
   auto tied = [=] __device__(uint64_t k) -> uint64_t { return (k > 0 && keys[k] == keys[k - 1]) ? 1u : 0u; };
   const uint64_t ties = scan_total<uint64_t, OpSum>(eng, n, tied);
   eng.stats.tied_after_key_sort = ties;
   clock.mark();  // 3
 
   if (ties == 0) {
+    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, log2_bits);
     clock.mark();  // 4
     clock.mark();  // 5
   } else {
@@ -366,6 +374,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
         h <<= 1;
       }
     }
+    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, log2_bits);
     clock.mark();  // 4
 
     // ---- 5. LCP of the tied neighbours: permuted-LCP recurrence on the deep positions ----
