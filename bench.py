@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — SA+LCP construction throughput (BASELINE.json metric: suffixes/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--n SIZE]
+                    [--impl ours|reference]
+
+A step is one full construction (text -> SA + LCP) of the named synthetic text.
+  value : suffixes/s with the text already resident in HBM and SA/LCP left in HBM
+          (device-resident entry point, CUDA events on the stream the kernels run on).
+  e2e   : suffixes/s through the reference-facing host-buffer call
+          (caps_sa_gpu_construct_u32: pinned host text -> H2D -> construct -> D2H SA+LCP),
+          copies inside the timed region.
+  roofline     : the dominant kernel (radix_scatter_kernel), per-launch CUDA-event times
+                 gathered inside the library during the timed steps.
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref, OpenMP stand-in for ParlayLib) timed
+                 on the box's host cores on a bounded prefix of the same text (rank 0, N=1).
+--impl reference runs only that CPU arm, K+W times, and prints its own JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import __graft_entry__ as graft  # noqa: E402
+
+WORKLOADS = {
+    # BASELINE.json configs[2]: the configuration the metric is quoted on (fits one B200)
+    "genome3g": dict(n=3_100_000_000, kind="genome_like", seed=3,
+                     desc="3.1 Gbp synthetic genome: uniform ACGT + injected repeats (SURVEY §8d config 3), 32-bit indices"),
+    # BASELINE.json configs[1]
+    "random100m": dict(n=100_000_001, kind="random_acgt_nl", seed=1,
+                       desc="100 Mbp uniform random ACGT + newline mapped to C (config 2)"),
+    "genome100m": dict(n=100_000_000, kind="genome_like", seed=3, desc="config 3 scaled to 100 Mbp"),
+}
+CPU_SAMPLE = 32_000_000   # prefix of the workload the CPU reference is timed on
+CPU_SUBPROBLEMS = 256      # the reference's best case in SURVEY.md §6 (default 8192 is ~2x slower)
+
+
+def make_text(pkg, spec, n):
+    kind = spec["kind"]
+    if kind == "genome_like":
+        return pkg.synth.genome_like(n, seed=spec["seed"], scale=n / 3.1e9)
+    if kind == "random_acgt_nl":
+        t = pkg.synth.random_acgt_chunked(n, spec["seed"])
+        t[-1] = ord("C")  # the CLI maps the trailing newline of gen_rand_seq.py's output to 'C'
+        return t
+    raise ValueError(kind)
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows = []
+        self.proc = None
+        self.index = device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])), smax.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_reference_run(text, subproblems, threads):
+    """One construct() of the unmodified reference on `text`; returns seconds (the region
+    the reference itself times, src/Suffix_Array.cpp:466-494)."""
+    import oracle_lib
+
+    os.environ["PARLAY_NUM_THREADS"] = str(threads)
+    if oracle_lib.ref() is not None:
+        _, _, secs = oracle_lib.ref_sa_lcp(text, subproblems=subproblems)
+        return secs, "reference"
+    t0 = time.time()
+    oracle_lib.port_sa_lcp(text, subproblems=subproblems)
+    return time.time() - t0, "port"
+
+
+def run_reference_arm(args, spec, n):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pkg = graft.load_package()
+    sample_n = min(n, args.cpu_sample)
+    text = make_text(pkg, spec, sample_n)  # same recipe, sample-sized
+    threads = os.cpu_count() or 1
+    times = []
+    kind = "reference"
+    for _ in range(args.warmup):
+        cpu_reference_run(text, args.cpu_subproblems, threads)
+    for _ in range(args.steps):
+        secs, kind = cpu_reference_run(text, args.cpu_subproblems, threads)
+        times.append(secs)
+    per_step = float(np.mean(times))
+    value = sample_n / per_step
+    line = {
+        "impl": "reference", "metric": "sa_lcp_suffixes_per_sec", "value": value, "unit": "suffixes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']}", "n": n, "idx_bytes": 4},
+        "cpu_baseline": {"value": value, "unit": "suffixes/s", "cores": threads, "kind": kind,
+                         "sample": f"first {sample_n} symbols of the workload recipe, subproblem_count={args.cpu_subproblems}, "
+                                   f"PARLAY_NUM_THREADS={threads} (OpenMP stand-in for ParlayLib), construct() only"},
+        "e2e": {"value": value, "unit": "suffixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="genome3g", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=float, default=None, help="override the text length")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-sample", type=int, default=CPU_SAMPLE)
+    ap.add_argument("--cpu-subproblems", type=int, default=CPU_SUBPROBLEMS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    spec = WORKLOADS[args.workload]
+    n = int(args.n) if args.n else spec["n"]
+
+    if args.impl == "reference":
+        run_reference_arm(args, spec, n)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pkg = graft.load_package()
+    if world > 1:
+        from caps_sa_b200 import multi_gpu  # sharded path (torch.distributed plumbing + our kernels)
+        return multi_gpu.bench_main(args, spec, n, pkg)
+
+    t_gen = time.time()
+    text_np = make_text(pkg, spec, n)
+    gen_s = time.time() - t_gen
+
+    eng = pkg.Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+
+    # pinned host buffers (the class shell allocates its SA_/LCP_ the same way)
+    text_pin = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    text_pin.numpy()[:] = text_np
+    sa_pin = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    lcp_pin = torch.empty(n, dtype=torch.int32, pin_memory=True)
+    text_host = text_pin.numpy()
+    sa_host = sa_pin.numpy().view(np.uint32)
+    lcp_host = lcp_pin.numpy().view(np.uint32)
+
+    d_text = torch.empty(n, dtype=torch.uint8, device="cuda")
+    d_text.copy_(text_pin, non_blocking=True)
+    d_sa = torch.empty(n, dtype=torch.int32, device="cuda")
+    d_lcp = torch.empty(n, dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+
+    def device_step():
+        eng.construct_device(d_text.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), 4, stream.cuda_stream)
+
+    def e2e_step():
+        eng.construct(text_host, sa_host, lcp_host)
+
+    # ---- device-resident: `value` ---------------------------------------------------------
+    for _ in range(args.warmup):
+        device_step()
+    eng.set_kernel_timing(True)
+    sampler = ClockSampler(local_rank)
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    scatter_ms, scatter_launches, scatter_bytes = 0.0, 0, 0
+    stage_ms = {}
+    ev0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+        st = eng.stats()
+        launches += st["kernel_launches"]
+        scatter_ms += st["ms_scatter"]
+        scatter_launches += st["scatter_launches"]
+        scatter_bytes += st["scatter_bytes"]
+        for k in ("ms_pack", "ms_sort", "ms_heads", "ms_refine", "ms_deep_lcp", "ms_total"):
+            stage_ms[k] = stage_ms.get(k, 0.0) + st[k] / args.steps
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    last_stats = eng.stats()
+    eng.set_kernel_timing(False)
+
+    # ---- end to end through the host-buffer C-ABI call: `e2e` ------------------------------
+    for _ in range(max(1, args.warmup - 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record(stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    ev3.record(stream)
+    torch.cuda.synchronize()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    e2e_ms = max(ev2.elapsed_time(ev3) / args.steps, e2e_wall_ms)
+    clocks = sampler.stop()
+
+    # sanity: the e2e result equals the device-resident result (same kernels)
+    same = bool(torch.equal(d_sa.cpu()[:1_000_000], sa_pin[:1_000_000]))
+
+    peak, peak_kind = load_peaks()
+    achieved = (scatter_bytes / 1e9) / (scatter_ms / 1e3) if scatter_ms > 0 else None
+    roofline = {
+        "kernel": "radix_scatter_kernel", "bound": "hbm",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+        "peak_source": peak_kind, "traffic": None,
+        "launches_timed": scatter_launches, "avg_launch_ms": scatter_ms / max(1, scatter_launches),
+        "share_of_step": scatter_ms / args.steps / dev_ms,
+        "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches),
+        "pipeline_frac": (n * 9 / 1e9) / (dev_ms / 1e3) / peak,  # 9 B/suffix compulsory traffic
+    }
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sample_n = min(n, args.cpu_sample)
+        threads = os.cpu_count() or 1
+        secs, kind = cpu_reference_run(text_np[:sample_n].copy(), args.cpu_subproblems, threads)
+        cpu_baseline = {"value": sample_n / secs, "unit": "suffixes/s", "cores": threads, "kind": kind,
+                        "seconds": secs,
+                        "sample": f"first {sample_n} symbols of the workload text, subproblem_count={args.cpu_subproblems}, "
+                                  f"PARLAY_NUM_THREADS={threads} (OpenMP stand-in for ParlayLib), construct() only"}
+
+    line = {
+        "metric": "sa_lcp_suffixes_per_sec", "value": n / (dev_ms / 1e3), "unit": "suffixes/s",
+        "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']}", "n": n, "idx_bytes": 4,
+                   "bits_per_symbol": last_stats["bits_per_symbol"], "l2": "inputs >> 126 MB L2, no explicit flush",
+                   "text_generation_s": round(gen_s, 1), "tied_after_key_sort": last_stats["tied_after_key_sort"],
+                   "refine_rounds": last_stats["refine_rounds"]},
+        "e2e": {"value": n / (e2e_ms / 1e3), "unit": "suffixes/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": n, "d2h_bytes_per_step": 2 * 4 * n, "matches_device_result": same},
+        "gpu_launches": int(launches),
+        "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,7 +27,8 @@ LIB_PATH = os.path.join(_PKG, "lib", "libcaps_sa_gpu.so")
 
 EXPORTED_SYMBOLS = [
     "caps_sa_gpu_device_count", "caps_sa_gpu_last_error", "caps_sa_gpu_engine_create",
-    "caps_sa_gpu_engine_destroy", "caps_sa_gpu_engine_stats", "caps_sa_gpu_construct_u32",
+    "caps_sa_gpu_engine_destroy", "caps_sa_gpu_engine_stats", "caps_sa_gpu_engine_set_stream",
+    "caps_sa_gpu_engine_set_kernel_timing", "caps_sa_gpu_construct_u32",
     "caps_sa_gpu_construct_u64", "caps_sa_gpu_construct_device_u32", "caps_sa_gpu_construct_device_u64",
     "caps_sa_gpu_map_acgt", "caps_sa_gpu_host_alloc", "caps_sa_gpu_host_free", "caps_sa_gpu_stage_pack",
     "caps_sa_gpu_stage_radix_sort_u64_u32", "caps_sa_gpu_stage_scan_u32",
@@ -41,7 +42,8 @@ class Stats(C.Structure):
                 ("deep_lcp_long", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("ms_pack", C.c_float), ("ms_sort", C.c_float), ("ms_heads", C.c_float),
                 ("ms_refine", C.c_float), ("ms_deep_lcp", C.c_float), ("ms_total", C.c_float),
-                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("scatter_launches", C.c_uint32),
+                ("ms_scatter", C.c_float), ("scatter_bytes", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -69,6 +71,8 @@ def lib():
         L.caps_sa_gpu_engine_destroy.argtypes = [p]
         L.caps_sa_gpu_engine_destroy.restype = None
         L.caps_sa_gpu_engine_stats.argtypes = [p, C.POINTER(Stats)]
+        L.caps_sa_gpu_engine_set_stream.argtypes = [p, p]
+        L.caps_sa_gpu_engine_set_kernel_timing.argtypes = [p, i32]
         for name in ("caps_sa_gpu_construct_u32", "caps_sa_gpu_construct_u64"):
             getattr(L, name).argtypes = [p, p, u64, p, p, u64, u64]
         for name in ("caps_sa_gpu_construct_device_u32", "caps_sa_gpu_construct_device_u64"):
@@ -144,6 +148,13 @@ class Engine:
         _check(lib().caps_sa_gpu_engine_stats(self._h, C.byref(s)))
         return s.as_dict()
 
+    def set_stream(self, stream: int | None) -> None:
+        """Issue all work on the given cudaStream_t (e.g. torch's current stream); None = own."""
+        _check(lib().caps_sa_gpu_engine_set_stream(self._h, stream or None))
+
+    def set_kernel_timing(self, enabled: bool) -> None:
+        _check(lib().caps_sa_gpu_engine_set_kernel_timing(self._h, int(enabled)))
+
     # -- host-buffer construction ---------------------------------------------------------
     def construct(self, text: np.ndarray, sa_out: np.ndarray, lcp_out: np.ndarray,
                   subproblem_count: int = 0, max_context: int = 0) -> None:
@@ -218,7 +229,10 @@ class SuffixArray:
         self._p = subproblem_count
         self._ctx = max_context
         self._engine = engine
-        self._sa_mem = self._lcp_mem = None
+        # result arrays are allocated here, as the reference allocates SA_/LCP_ in its
+        # constructor (src/Suffix_Array.cpp:20-21); pinned so the D2H copy runs at PCIe speed
+        self._sa_mem = PinnedArray(self._n, self._dtype)
+        self._lcp_mem = PinnedArray(self._n, self._dtype)
         self._built = False
 
     def T(self) -> np.ndarray:
@@ -229,8 +243,6 @@ class SuffixArray:
 
     def construct(self) -> None:
         eng = self._engine or default_engine()
-        self._sa_mem = PinnedArray(self._n, self._dtype)
-        self._lcp_mem = PinnedArray(self._n, self._dtype)
         eng.construct(self._text, self._sa_mem.array, self._lcp_mem.array, self._p, self._ctx)
         self._stats = eng.stats()
         self._built = True

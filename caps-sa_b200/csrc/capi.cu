@@ -151,6 +151,21 @@ int caps_sa_gpu_engine_stats(const caps_sa_gpu_engine* engine, caps_sa_gpu_stats
   out->ms_pack = s.ms_pack, out->ms_sort = s.ms_sort, out->ms_heads = s.ms_heads;
   out->ms_refine = s.ms_refine, out->ms_deep_lcp = s.ms_deep_lcp, out->ms_total = s.ms_total;
   out->ms_h2d = s.ms_h2d, out->ms_d2h = s.ms_d2h;
+  out->scatter_launches = s.scatter_launches;
+  out->ms_scatter = s.ms_scatter;
+  out->scatter_bytes = s.scatter_bytes;
+  return CAPS_SA_GPU_OK;
+}
+
+int caps_sa_gpu_engine_set_stream(caps_sa_gpu_engine* engine, void* stream) {
+  if (!engine) return bad_args("engine is NULL");
+  engine->impl.stream = stream ? static_cast<cudaStream_t>(stream) : engine->impl.own_stream;
+  return CAPS_SA_GPU_OK;
+}
+
+int caps_sa_gpu_engine_set_kernel_timing(caps_sa_gpu_engine* engine, int enabled) {
+  if (!engine) return bad_args("engine is NULL");
+  engine->impl.radix.timer.enabled = enabled != 0;
   return CAPS_SA_GPU_OK;
 }
 

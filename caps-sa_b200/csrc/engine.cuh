@@ -23,6 +23,9 @@ struct Stats {
   uint64_t kernel_launches = 0;
   float ms_pack = 0, ms_sort = 0, ms_heads = 0, ms_refine = 0, ms_deep_lcp = 0, ms_total = 0;
   float ms_h2d = 0, ms_d2h = 0;
+  uint32_t scatter_launches = 0;
+  float ms_scatter = 0;
+  uint64_t scatter_bytes = 0;
 };
 
 struct PackedTextBuf {
@@ -35,8 +38,8 @@ struct PackedTextBuf {
 
 struct Engine {
   DeviceInfo dev;
-  cudaStream_t stream = nullptr;
-  bool owns_stream = false;
+  cudaStream_t stream = nullptr;      // stream all work is issued on
+  cudaStream_t own_stream = nullptr;  // created with the engine
   RadixScratch radix;
   ScanScratch<uint32_t> scan32;
   ScanScratch<uint64_t> scan64;

@@ -13,6 +13,8 @@
 // unsorted key array.
 #pragma once
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace capsb {
@@ -36,6 +38,7 @@ struct ArraySource {
   const ValT* vals;
   __device__ __forceinline__ KeyT key(uint64_t i) const { return keys[i]; }
   __device__ __forceinline__ ValT val(uint64_t i) const { return vals[i]; }
+  static constexpr uint64_t bytes_read_per_item() { return sizeof(KeyT) + sizeof(ValT); }
 };
 
 // Kernels -------------------------------------------------------------------------------
@@ -75,43 +78,57 @@ static __global__ void __launch_bounds__(kScanThreads) radix_offsets_kernel(uint
   if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
 }
 
-template <class KeyT, class ValT, class Src>
-__global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(Src src, uint64_t n, uint64_t chunk,
-                                                                   unsigned shift,
-                                                                   const uint64_t* __restrict__ hist,
-                                                                   const uint64_t* __restrict__ digit_total,
-                                                                   KeyT* __restrict__ keys_out,
-                                                                   ValT* __restrict__ vals_out) {
-  __shared__ uint64_t run_base[kRadixSize];          // next free global slot per digit for this CTA
-  __shared__ uint64_t tile_base[kRadixSize];         // run_base at the start of the current tile
-  __shared__ unsigned warp_cnt[kRsWarps][kRadixSize + 1];  // [..][256] collects out-of-range lanes
-  __shared__ uint64_t scan_smem[kScanThreads / 32];
+// Shared-memory layout of the scatter kernel (dynamic: > 48 KB for 64-bit keys).
+template <class KeyT, class ValT>
+struct ScatterSmem {
+  KeyT keys[kRsTile];   // the tile in digit-sorted order
+  ValT vals[kRsTile];
+  uint64_t run_base[kRadixSize];    // next free global slot per digit for this CTA
+  uint64_t out_shift[kRadixSize];   // global slot of tile-sorted position s is out_shift[digit] + s
+  unsigned digit_start[kRadixSize]; // first tile-sorted position of each digit
+  unsigned warp_cnt[kRsWarps][kRadixSize + 1];  // [..][256] collects out-of-range lanes
+  uint64_t scan_tmp[kScanThreads / 32];
+};
 
+// Tile pipeline: coalesced loads -> stable in-tile ranking (warp match_any + per-warp
+// counters + a 256-wide block scan) -> tile reordered by digit in shared memory -> coalesced
+// runs written to each digit's global range.  Only full sectors leave the SM except at run
+// boundaries, so HBM sees ~1x the algorithmic write traffic.
+template <class KeyT, class ValT, class Src>
+__global__ void __launch_bounds__(kRsThreads, 2) radix_scatter_kernel(Src src, uint64_t n, uint64_t chunk,
+                                                                      unsigned shift,
+                                                                      const uint64_t* __restrict__ hist,
+                                                                      const uint64_t* __restrict__ digit_total,
+                                                                      KeyT* __restrict__ keys_out,
+                                                                      ValT* __restrict__ vals_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem<KeyT, ValT>& sm = *reinterpret_cast<ScatterSmem<KeyT, ValT>*>(smem_raw);
+
+  const unsigned tid = threadIdx.x;
   const unsigned lane = lane_id();
-  const unsigned warp = threadIdx.x >> 5;
+  const unsigned warp = tid >> 5;
   const unsigned lt = lanemask_lt();
 
   {  // global base of digit d = sum of totals of smaller digits; plus this CTA's row offset
-    const uint64_t t = digit_total[threadIdx.x];
+    const uint64_t t = digit_total[tid];
     uint64_t inc, total;
-    const uint64_t excl = block_scan<uint64_t, OpSum>(t, &inc, &total, scan_smem);
-    run_base[threadIdx.x] = excl + hist[static_cast<uint64_t>(threadIdx.x) * gridDim.x + blockIdx.x];
+    const uint64_t excl = block_scan<uint64_t, OpSum>(t, &inc, &total, sm.scan_tmp);
+    sm.run_base[tid] = excl + hist[static_cast<uint64_t>(tid) * gridDim.x + blockIdx.x];
   }
-  __syncthreads();
 
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
 
   for (uint64_t tile = begin; tile < end; tile += kRsTile) {
-    for (int i = threadIdx.x; i < kRsWarps * (kRadixSize + 1); i += kRsThreads) (&warp_cnt[0][0])[i] = 0;
-    __syncthreads();
+    for (int i = tid; i < kRsWarps * (kRadixSize + 1); i += kRsThreads) (&sm.warp_cnt[0][0])[i] = 0;
+    __syncthreads();  // also orders the previous tile's shared-memory reads before new writes
 
     // warp-striped layout keeps global loads coalesced and defines the stable order:
     // (warp, item, lane) lexicographic == increasing input index.
     const uint64_t warp_first = tile + static_cast<uint64_t>(warp) * (32 * kRsItems);
     KeyT key[kRsItems];
-    unsigned dig[kRsItems];
-    unsigned rank[kRsItems];
+    ValT val[kRsItems];
+    unsigned dig[kRsItems];  // digit in the low 16 bits, in-warp rank in the high 16 bits
 #pragma unroll
     for (int t = 0; t < kRsItems; ++t) {
       const uint64_t i = warp_first + static_cast<uint64_t>(t) * 32 + lane;
@@ -121,51 +138,113 @@ __global__ void __launch_bounds__(kRsThreads) radix_scatter_kernel(Src src, uint
     }
 #pragma unroll
     for (int t = 0; t < kRsItems; ++t) {
+      const uint64_t i = warp_first + static_cast<uint64_t>(t) * 32 + lane;
+      val[t] = i < end ? src.val(i) : ValT(0);
+    }
+#pragma unroll
+    for (int t = 0; t < kRsItems; ++t) {
       const unsigned peers = __match_any_sync(0xffffffffu, dig[t]);
       const int leader = __ffs(static_cast<int>(peers)) - 1;
       unsigned before = 0;
       if (static_cast<int>(lane) == leader) {
-        before = warp_cnt[warp][dig[t]];
-        warp_cnt[warp][dig[t]] = before + __popc(peers);
+        before = sm.warp_cnt[warp][dig[t]];
+        sm.warp_cnt[warp][dig[t]] = before + __popc(peers);
       }
       before = __shfl_sync(0xffffffffu, before, leader);
-      rank[t] = before + __popc(peers & lt);
+      dig[t] |= (before + __popc(peers & lt)) << 16;
       __syncwarp();
     }
     __syncthreads();
 
-    {  // digit threadIdx.x: exclusive scan over warps, then advance the CTA's running base
+    {  // digit `tid`: exclusive scan over warps, digit starts inside the tile, global shifts
       unsigned run = 0;
 #pragma unroll
       for (int w = 0; w < kRsWarps; ++w) {
-        const unsigned c = warp_cnt[w][threadIdx.x];
-        warp_cnt[w][threadIdx.x] = run;
+        const unsigned c = sm.warp_cnt[w][tid];
+        sm.warp_cnt[w][tid] = run;
         run += c;
       }
-      const uint64_t base = run_base[threadIdx.x];
-      tile_base[threadIdx.x] = base;
-      run_base[threadIdx.x] = base + run;
+      uint64_t inc, total;
+      const uint64_t start = block_scan<uint64_t, OpSum>(static_cast<uint64_t>(run), &inc, &total, sm.scan_tmp);
+      const uint64_t base = sm.run_base[tid];
+      sm.digit_start[tid] = static_cast<unsigned>(start);
+      sm.out_shift[tid] = base - start;  // modular arithmetic: out_shift + s is exact
+      sm.run_base[tid] = base + run;
     }
     __syncthreads();
 
 #pragma unroll
     for (int t = 0; t < kRsItems; ++t) {
-      if (dig[t] < static_cast<unsigned>(kRadixSize)) {
-        const uint64_t i = warp_first + static_cast<uint64_t>(t) * 32 + lane;
-        const uint64_t pos = tile_base[dig[t]] + warp_cnt[warp][dig[t]] + rank[t];
-        keys_out[pos] = key[t];
-        vals_out[pos] = src.val(i);
+      const unsigned d = dig[t] & 0xFFFFu;
+      if (d < static_cast<unsigned>(kRadixSize)) {
+        const unsigned s = sm.digit_start[d] + sm.warp_cnt[warp][d] + (dig[t] >> 16);
+        sm.keys[s] = key[t];
+        sm.vals[s] = val[t];
       }
     }
     __syncthreads();
+
+    const unsigned valid = static_cast<unsigned>(end - tile < kRsTile ? end - tile : kRsTile);
+#pragma unroll
+    for (int t = 0; t < kRsItems; ++t) {
+      const unsigned s = static_cast<unsigned>(t) * kRsThreads + tid;
+      if (s < valid) {
+        const KeyT k = sm.keys[s];
+        const uint64_t pos = sm.out_shift[radix_digit<KeyT>(k, shift)] + s;
+        keys_out[pos] = k;
+        vals_out[pos] = sm.vals[s];
+      }
+    }
   }
 }
 
 // Host driver ---------------------------------------------------------------------------
+// Optional per-launch timing of the scatter kernel (the dominant kernel of the pipeline).
+struct KernelTimer {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;                             // recycled events
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;  // recorded, not yet read
+  uint64_t bytes = 0;
+  cudaEvent_t get() {
+    cudaEvent_t e;
+    if (!pool.empty()) {
+      e = pool.back();
+      pool.pop_back();
+    } else {
+      CAPSB_CUDA(cudaEventCreate(&e));
+    }
+    return e;
+  }
+  // Sums and recycles the pending intervals (call after the stream has been synchronised).
+  float drain(uint32_t* launches) {
+    float total = 0;
+    for (auto& pr : pending) {
+      float ms = 0;
+      CAPSB_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+      total += ms;
+      pool.push_back(pr.first);
+      pool.push_back(pr.second);
+    }
+    *launches = static_cast<uint32_t>(pending.size());
+    pending.clear();
+    return total;
+  }
+  void reset() {
+    uint32_t ignored;
+    if (!pending.empty()) drain(&ignored);
+    bytes = 0;
+  }
+  ~KernelTimer() {
+    for (auto& pr : pending) cudaEventDestroy(pr.first), cudaEventDestroy(pr.second);
+    for (cudaEvent_t e : pool) cudaEventDestroy(e);
+  }
+};
+
 struct RadixScratch {
   DevBuf<uint64_t> hist;         // [256][blocks]
   DevBuf<uint64_t> digit_total;  // [256]
   unsigned max_blocks = 0;
+  KernelTimer timer;
   void init(const DeviceInfo& dev, cudaStream_t stream) {
     max_blocks = static_cast<unsigned>(dev.sm_count) * 4;
     hist.alloc(static_cast<uint64_t>(kRadixSize) * max_blocks, stream);
@@ -183,8 +262,26 @@ inline void radix_pass(cudaStream_t stream, RadixScratch& rs, Src src, uint64_t 
                rs.hist.get());
   CAPSB_LAUNCH(radix_offsets_kernel, kRadixSize, kScanThreads, 0, stream, rs.hist.get(), ck.blocks,
                rs.digit_total.get());
-  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src>), ck.blocks, kRsThreads, 0, stream, src, n, ck.chunk,
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (rs.timer.enabled) {
+    t0 = rs.timer.get();
+    t1 = rs.timer.get();
+    CAPSB_CUDA(cudaEventRecord(t0, stream));
+  }
+  constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT>);
+  static bool configured = false;  // per template instantiation
+  if (!configured) {
+    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
+    configured = true;
+  }
+  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src>), ck.blocks, kRsThreads, kSmem, stream, src, n, ck.chunk,
                shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
+  if (rs.timer.enabled) {
+    CAPSB_CUDA(cudaEventRecord(t1, stream));
+    rs.timer.pending.emplace_back(t0, t1);
+    rs.timer.bytes += n * (sizeof(KeyT) + sizeof(ValT)) + n * Src::bytes_read_per_item();
+  }
 }
 
 // Sorts (keys, vals) by the key bits [begin_bit, end_bit) using ping-pong buffers.

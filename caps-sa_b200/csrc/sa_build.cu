@@ -24,8 +24,8 @@ Engine::Engine(int device) {
   cudaDeviceProp prop;
   CAPSB_CUDA(cudaGetDeviceProperties(&prop, device));
   dev.sm_count = prop.multiProcessorCount;
-  CAPSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-  owns_stream = true;
+  CAPSB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+  stream = own_stream;
   // keep freed scratch cached in the pool between constructions
   cudaMemPool_t pool;
   CAPSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -38,12 +38,12 @@ Engine::Engine(int device) {
 
 Engine::~Engine() {
   cudaSetDevice(dev.device);
-  if (stream) cudaStreamSynchronize(stream);
+  if (own_stream) cudaStreamSynchronize(own_stream);
   radix = RadixScratch();
   scan32 = ScanScratch<uint32_t>();
   scan64 = ScanScratch<uint64_t>();
   for (cudaEvent_t e : events) cudaEventDestroy(e);
-  if (owns_stream && stream) cudaStreamDestroy(stream);
+  if (own_stream) cudaStreamDestroy(own_stream);
 }
 
 namespace {
@@ -74,6 +74,8 @@ struct TextSource {
   PackedText pt;
   __device__ __forceinline__ uint64_t key(uint64_t i) const { return pt.window(i); }
   __device__ __forceinline__ IdxT val(uint64_t i) const { return static_cast<IdxT>(i); }
+  // the text window is re-read from L1/L2; compulsory traffic is the packed text itself (< 1 B)
+  static constexpr uint64_t bytes_read_per_item() { return 1; }
 };
 
 // Stage timer: records an event now; elapsed times are read at the end.
@@ -206,6 +208,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   const DeviceInfo& dev = eng.dev;
   const uint64_t launches_before = g_kernel_launches.load();
   eng.stats = Stats();
+  eng.radix.timer.reset();
   eng.stats.n = n;
   eng.stats.idx_bytes = sizeof(IdxT);
   if (n == 0) return;
@@ -458,6 +461,10 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   eng.stats.ms_deep_lcp = clock.between(4, 5);
   eng.stats.ms_total = clock.between(0, 6);
   eng.stats.kernel_launches = g_kernel_launches.load() - launches_before;
+  if (eng.radix.timer.enabled) {
+    eng.stats.scatter_bytes = eng.radix.timer.bytes;
+    eng.stats.ms_scatter = eng.radix.timer.drain(&eng.stats.scatter_launches);
+  }
 }
 
 void stage_scan_u32(Engine& eng, const uint32_t* d_in, uint32_t* d_out, uint64_t n, bool inclusive_max) {

@@ -73,29 +73,31 @@ def genome_like(n: int, seed: int = 3, scale: float | None = None) -> np.ndarray
     text = random_acgt_chunked(n, seed)
     rng = np.random.default_rng([seed, 0xC0FFEE])
 
-    def mutate(seq: np.ndarray, rate: float) -> np.ndarray:
-        out = seq.copy()
-        hits = rng.random(len(seq)) < rate
-        k = int(hits.sum())
-        if k:
-            out[hits] = _ACGT[rng.integers(0, 4, size=k, dtype=np.uint8)]
-        return out
-
     def place(seq: np.ndarray) -> None:
         if len(seq) >= n:
             return
         at = int(rng.integers(0, n - len(seq)))
         text[at:at + len(seq)] = seq
 
-    def families(count: int, length: int) -> list[np.ndarray]:
-        return [_ACGT[rng.integers(0, 4, size=length, dtype=np.uint8)] for _ in range(count)]
+    def scatter_family_copies(copies: int, families: int, length: int, rate: float, batch: int) -> None:
+        """`copies` mutated copies of `families` random consensus sequences, vectorised."""
+        if length >= n:
+            return
+        consensus = _ACGT[rng.integers(0, 4, size=(families, length), dtype=np.uint8)]
+        offs = np.arange(length, dtype=np.int64)
+        for lo in range(0, copies, batch):
+            cnt = min(batch, copies - lo)
+            fam = rng.integers(0, families, size=cnt)
+            at = rng.integers(0, n - length, size=cnt)
+            block = consensus[fam]
+            hit = rng.random((cnt, length)) < rate
+            k = int(hit.sum())
+            if k:
+                block[hit] = _ACGT[rng.integers(0, 4, size=k, dtype=np.uint8)]
+            text[(at[:, None] + offs[None, :]).reshape(-1)] = block.reshape(-1)
 
-    short_fams = families(50, 300)
-    for _ in range(max(1, int(1_000_000 * scale))):
-        place(mutate(short_fams[int(rng.integers(0, 50))], 0.10))
-    long_fams = families(5, 6000)
-    for _ in range(max(1, int(5_000 * scale))):
-        place(mutate(long_fams[int(rng.integers(0, 5))], 0.02))
+    scatter_family_copies(max(1, int(1_000_000 * scale)), 50, 300, 0.10, 100_000)
+    scatter_family_copies(max(1, int(5_000 * scale)), 5, 6000, 0.02, 1_000)
     for _ in range(max(1, int(200 * scale))):
         seg_len = min(100_000, n // 8)
         src = int(rng.integers(0, n - seg_len))

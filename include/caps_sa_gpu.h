@@ -47,6 +47,11 @@ typedef struct caps_sa_gpu_stats {
   uint64_t kernel_launches;     /* launches of this library's kernels */
   float ms_pack, ms_sort, ms_heads, ms_refine, ms_deep_lcp, ms_total;
   float ms_h2d, ms_d2h;         /* host-buffer entry points only */
+  /* Dominant kernel (radix_scatter_kernel), measured with CUDA events around each launch when
+   * kernel timing is enabled (caps_sa_gpu_engine_set_kernel_timing): */
+  uint32_t scatter_launches;
+  float ms_scatter;             /* summed duration of those launches */
+  uint64_t scatter_bytes;       /* summed algorithmic bytes (keys+values read once, written once) */
 } caps_sa_gpu_stats;
 
 /* Number of CUDA devices visible to the library (0 if none / driver missing). */
@@ -59,6 +64,13 @@ const char* caps_sa_gpu_last_error(void);
 caps_sa_gpu_engine* caps_sa_gpu_engine_create(int device);
 void caps_sa_gpu_engine_destroy(caps_sa_gpu_engine* engine);
 int caps_sa_gpu_engine_stats(const caps_sa_gpu_engine* engine, caps_sa_gpu_stats* out);
+
+/* Run all of the engine's work on `stream` (a cudaStream_t; NULL = the engine's own stream),
+ * so that a caller's CUDA events on that stream bracket the work. */
+int caps_sa_gpu_engine_set_stream(caps_sa_gpu_engine* engine, void* stream);
+
+/* Enable/disable per-launch CUDA-event timing of the dominant kernel (off by default). */
+int caps_sa_gpu_engine_set_kernel_timing(caps_sa_gpu_engine* engine, int enabled);
 
 /* ---- Host-buffer construction: what Suffix_Array<idx_t>::construct() binds --------------
  * Replaces the reference's construct() (src/Suffix_Array.cpp:466-494).  `text` is borrowed
