@@ -190,7 +190,10 @@ def main():
     pkg = graft.load_package()
     if world > 1:
         from caps_sa_b200 import multi_gpu  # sharded path (torch.distributed plumbing + our kernels)
-        return multi_gpu.bench_main(args, spec, n, pkg)
+        multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     t_gen = time.time()
     text_np = make_text(pkg, spec, n)

@@ -32,7 +32,12 @@ EXPORTED_SYMBOLS = [
     "caps_sa_gpu_construct_u64", "caps_sa_gpu_construct_device_u32", "caps_sa_gpu_construct_device_u64",
     "caps_sa_gpu_map_acgt", "caps_sa_gpu_host_alloc", "caps_sa_gpu_host_free", "caps_sa_gpu_stage_pack",
     "caps_sa_gpu_stage_radix_sort_u64_u32", "caps_sa_gpu_stage_scan_u32",
+    "caps_sa_gpu_construct_multi_u32", "caps_sa_gpu_construct_multi_u64", "caps_sa_gpu_comm_unique_id",
+    "caps_sa_gpu_engine_comm_init", "caps_sa_gpu_construct_sharded_device_u32",
+    "caps_sa_gpu_construct_sharded_device_u64", "caps_sa_gpu_construct_sharded_u32",
+    "caps_sa_gpu_construct_sharded_u64", "caps_sa_gpu_shard_copy",
 ]
+COMM_ID_BYTES = 128
 
 
 class Stats(C.Structure):
@@ -43,7 +48,9 @@ class Stats(C.Structure):
                 ("ms_pack", C.c_float), ("ms_sort", C.c_float), ("ms_heads", C.c_float),
                 ("ms_refine", C.c_float), ("ms_deep_lcp", C.c_float), ("ms_total", C.c_float),
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("scatter_launches", C.c_uint32),
-                ("ms_scatter", C.c_float), ("scatter_bytes", C.c_uint64)]
+                ("ms_scatter", C.c_float), ("scatter_bytes", C.c_uint64), ("key_bits", C.c_uint32),
+                ("reserved", C.c_uint32), ("ms_partition", C.c_float), ("ms_merge", C.c_float),
+                ("comm_bytes", C.c_uint64), ("shard_offset", C.c_uint64), ("shard_count", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -85,6 +92,15 @@ def lib():
         L.caps_sa_gpu_stage_pack.argtypes = [p, p, u64, p, C.POINTER(u64), C.POINTER(u32)]
         L.caps_sa_gpu_stage_radix_sort_u64_u32.argtypes = [p, p, p, u64, C.c_uint, C.c_uint]
         L.caps_sa_gpu_stage_scan_u32.argtypes = [p, p, u64, i32]
+        for name in ("caps_sa_gpu_construct_multi_u32", "caps_sa_gpu_construct_multi_u64"):
+            getattr(L, name).argtypes = [C.POINTER(i32), i32, p, u64, p, p, u64, u64, C.POINTER(Stats)]
+        L.caps_sa_gpu_comm_unique_id.argtypes = [p]
+        L.caps_sa_gpu_engine_comm_init.argtypes = [p, p, i32, i32]
+        for name in ("caps_sa_gpu_construct_sharded_device_u32", "caps_sa_gpu_construct_sharded_device_u64"):
+            getattr(L, name).argtypes = [p, p, u64, p]
+        for name in ("caps_sa_gpu_construct_sharded_u32", "caps_sa_gpu_construct_sharded_u64"):
+            getattr(L, name).argtypes = [p, p, u64, p, p]
+        L.caps_sa_gpu_shard_copy.argtypes = [p, p, p, i32]
         _lib = L
     return _lib
 
@@ -173,6 +189,29 @@ class Engine:
               else lib().caps_sa_gpu_construct_device_u64)
         _check(fn(self._h, d_text, n, d_sa, d_lcp, stream))
 
+    # -- sharded construction, one process per GPU (see multi_gpu.py for the torchrun plumbing) --
+    def comm_init(self, comm_id: bytes, rank: int, world: int) -> None:
+        """Collective: joins the NCCL communicator described by the 128-byte id."""
+        assert len(comm_id) == COMM_ID_BYTES
+        buf = C.create_string_buffer(bytes(comm_id), COMM_ID_BYTES)
+        _check(lib().caps_sa_gpu_engine_comm_init(self._h, buf, rank, world))
+
+    def construct_sharded_device(self, d_text: int, n: int, idx_bytes: int = 4, stream: int = 0) -> None:
+        fn = (lib().caps_sa_gpu_construct_sharded_device_u32 if idx_bytes == 4
+              else lib().caps_sa_gpu_construct_sharded_device_u64)
+        _check(fn(self._h, d_text, n, stream))
+
+    def construct_sharded(self, text: np.ndarray, sa_out: np.ndarray, lcp_out: np.ndarray) -> None:
+        """Host buffers; this rank's shard lands at sa_out[offset:offset+count] (see stats())."""
+        assert text.dtype == np.uint8 and text.flags.c_contiguous
+        assert sa_out.dtype == lcp_out.dtype and sa_out.dtype in (np.uint32, np.uint64)
+        fn = (lib().caps_sa_gpu_construct_sharded_u32 if sa_out.dtype == np.uint32
+              else lib().caps_sa_gpu_construct_sharded_u64)
+        _check(fn(self._h, text.ctypes.data, len(text), sa_out.ctypes.data, lcp_out.ctypes.data))
+
+    def shard_copy(self, sa_dst: int, lcp_dst: int, to_host: bool) -> None:
+        _check(lib().caps_sa_gpu_shard_copy(self._h, sa_dst, lcp_dst, int(to_host)))
+
     def map_acgt(self, text: np.ndarray) -> None:
         assert text.dtype == np.uint8 and text.flags.c_contiguous and text.flags.writeable
         _check(lib().caps_sa_gpu_map_acgt(self._h, text.ctypes.data, len(text)))
@@ -202,6 +241,29 @@ class Engine:
         return data
 
 
+def comm_unique_id() -> bytes:
+    """A fresh NCCL unique id (rank 0 creates it, the host side broadcasts it)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().caps_sa_gpu_comm_unique_id(buf))
+    return buf.raw
+
+
+def construct_multi(text: np.ndarray, sa_out: np.ndarray, lcp_out: np.ndarray, devices,
+                    subproblem_count: int = 0, max_context: int = 0) -> list:
+    """Sharded construction inside one process: rank r runs on CUDA device devices[r] (a device
+    may be listed several times).  Returns the per-rank statistics."""
+    assert text.dtype == np.uint8 and text.flags.c_contiguous
+    assert sa_out.dtype == lcp_out.dtype and sa_out.dtype in (np.uint32, np.uint64)
+    n = len(text)
+    assert len(sa_out) == n and len(lcp_out) == n
+    devs = (C.c_int * len(devices))(*devices)
+    stats = (Stats * len(devices))()
+    fn = lib().caps_sa_gpu_construct_multi_u32 if sa_out.dtype == np.uint32 else lib().caps_sa_gpu_construct_multi_u64
+    _check(fn(devs, len(devices), text.ctypes.data, n, sa_out.ctypes.data, lcp_out.ctypes.data,
+              subproblem_count, max_context, stats))
+    return [s.as_dict() for s in stats]
+
+
 _default_engines: dict[int, Engine] = {}
 
 
@@ -218,7 +280,7 @@ class SuffixArray:
     unless idx_bytes is given.  The text is borrowed (kept alive by this object)."""
 
     def __init__(self, text, subproblem_count: int = 0, max_context: int = 0, idx_bytes: int | None = None,
-                 engine: Engine | None = None):
+                 engine: Engine | None = None, devices=None):
         if isinstance(text, (bytes, bytearray, memoryview)):
             text = np.frombuffer(bytes(text), dtype=np.uint8)
         self._text = np.ascontiguousarray(text, dtype=np.uint8)
@@ -229,6 +291,7 @@ class SuffixArray:
         self._p = subproblem_count
         self._ctx = max_context
         self._engine = engine
+        self._devices = list(devices) if devices is not None else None  # several ranks -> sharded path
         # result arrays are allocated here, as the reference allocates SA_/LCP_ in its
         # constructor (src/Suffix_Array.cpp:20-21); pinned so the D2H copy runs at PCIe speed
         self._sa_mem = PinnedArray(self._n, self._dtype)
@@ -242,9 +305,14 @@ class SuffixArray:
         return self._n
 
     def construct(self) -> None:
-        eng = self._engine or default_engine()
-        eng.construct(self._text, self._sa_mem.array, self._lcp_mem.array, self._p, self._ctx)
-        self._stats = eng.stats()
+        if self._devices is not None:
+            self._rank_stats = construct_multi(self._text, self._sa_mem.array, self._lcp_mem.array, self._devices,
+                                               self._p, self._ctx)
+            self._stats = self._rank_stats[0]
+        else:
+            eng = self._engine or default_engine()
+            eng.construct(self._text, self._sa_mem.array, self._lcp_mem.array, self._p, self._ctx)
+            self._stats = eng.stats()
         self._built = True
 
     def SA(self) -> np.ndarray:

@@ -16,7 +16,7 @@ OBJ_DIR = os.path.join(PKG, "build")
 BIN_DIR = os.path.join(ROOT, "bin")
 LIB_PATH = os.path.join(LIB_DIR, "libcaps_sa_gpu.so")
 
-CU_SOURCES = ["text_pack.cu", "sa_build.cu", "capi.cu"]
+CU_SOURCES = ["text_pack.cu", "sa_build.cu", "sharded_build.cu", "comm.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
               "--extended-lambda", "-Xcompiler", "-fPIC", "-diag-suppress", "186"]
 

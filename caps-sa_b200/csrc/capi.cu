@@ -3,8 +3,10 @@
 // device every entry point fails loudly.
 #include <cstring>
 #include <new>
+#include <thread>
 
 #include "../../include/caps_sa_gpu.h"
+#include "comm.cuh"
 #include "engine.cuh"
 
 using capsb::Engine;
@@ -106,6 +108,156 @@ int construct_device(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
   });
 }
 
+void fill_stats(const capsb::Stats& s, caps_sa_gpu_stats* out) {
+  out->n = s.n;
+  out->idx_bytes = s.idx_bytes;
+  out->bits_per_symbol = s.bits_per_symbol;
+  out->alphabet_size = s.alphabet_size;
+  out->refine_rounds = s.refine_rounds;
+  out->tied_after_key_sort = s.tied_after_key_sort;
+  out->deep_lcp_direct = s.deep_lcp_direct;
+  out->deep_lcp_long = s.deep_lcp_long;
+  out->kernel_launches = s.kernel_launches;
+  out->ms_pack = s.ms_pack, out->ms_sort = s.ms_sort, out->ms_heads = s.ms_heads;
+  out->ms_refine = s.ms_refine, out->ms_deep_lcp = s.ms_deep_lcp, out->ms_total = s.ms_total;
+  out->ms_h2d = s.ms_h2d, out->ms_d2h = s.ms_d2h;
+  out->scatter_launches = s.scatter_launches;
+  out->ms_scatter = s.ms_scatter;
+  out->scatter_bytes = s.scatter_bytes;
+  out->key_bits = s.key_bits;
+  out->reserved = 0;
+  out->ms_partition = s.ms_partition, out->ms_merge = s.ms_merge;
+  out->comm_bytes = s.comm_bytes;
+  out->shard_offset = s.shard_offset, out->shard_count = s.shard_count;
+}
+
+template <class IdxT>
+capsb::ShardResult<IdxT>& shard_of(Engine& eng);
+template <>
+capsb::ShardResult<uint32_t>& shard_of<uint32_t>(Engine& eng) { return eng.shard32; }
+template <>
+capsb::ShardResult<uint64_t>& shard_of<uint64_t>(Engine& eng) { return eng.shard64; }
+
+int check_context(uint64_t max_context, uint64_t n) {
+  if (max_context != 0 && max_context < n) {
+    g_last_error = "bounded context (max_context < n) is not supported by the GPU engine";
+    return CAPS_SA_GPU_ERR_UNSUPPORTED;
+  }
+  return CAPS_SA_GPU_OK;
+}
+
+// One process, one host thread per rank, peer copies between the ranks (ThreadComm).
+template <class IdxT>
+int construct_multi(const int* devices, int num_ranks, const char* text, uint64_t n, IdxT* sa_out, IdxT* lcp_out,
+                    uint64_t max_context, caps_sa_gpu_stats* stats_out) {
+  if (!devices || num_ranks < 1 || num_ranks > 64) return bad_args("bad device list");
+  if (n > 0 && (!text || !sa_out || !lcp_out)) return bad_args("NULL buffer");
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
+  if (const int rc = check_context(max_context, n)) return rc;
+  return guarded([&]() -> int {
+    int visible = 0;
+    CAPSB_CUDA(cudaGetDeviceCount(&visible));
+    for (int r = 0; r < num_ranks; ++r)
+      if (devices[r] < 0 || devices[r] >= visible)
+        capsb::fail("no such CUDA device: " + std::to_string(devices[r]) + " (visible: " + std::to_string(visible) + ")");
+    auto group = std::make_shared<capsb::ThreadGroup>(num_ranks);
+    std::vector<capsb::Stats> stats(num_ranks);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < num_ranks; ++r) {
+      threads.emplace_back([&, r] {
+        try {
+          Engine eng(devices[r]);
+          capsb::ThreadComm comm(group, r, devices[r]);
+          if (n) {
+            cudaStream_t st = eng.stream;
+            capsb::ShardResult<IdxT> shard;
+            {
+              capsb::DevBuf<uint8_t> d_text(n, st);
+              EventPair h2d;
+              CAPSB_CUDA(cudaEventRecord(h2d.a, st));
+              CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
+              CAPSB_CUDA(cudaEventRecord(h2d.b, st));
+              capsb::build_sa_lcp_sharded<IdxT>(eng, comm, d_text.get(), n, shard);
+              eng.stats.ms_h2d = h2d.ms();
+            }
+            EventPair d2h;
+            CAPSB_CUDA(cudaEventRecord(d2h.a, st));
+            if (shard.count) {
+              CAPSB_CUDA(cudaMemcpyAsync(sa_out + shard.offset, shard.sa.get(), shard.count * sizeof(IdxT),
+                                         cudaMemcpyDeviceToHost, st));
+              CAPSB_CUDA(cudaMemcpyAsync(lcp_out + shard.offset, shard.lcp.get(), shard.count * sizeof(IdxT),
+                                         cudaMemcpyDeviceToHost, st));
+            }
+            CAPSB_CUDA(cudaEventRecord(d2h.b, st));
+            CAPSB_CUDA(cudaStreamSynchronize(st));
+            eng.stats.ms_d2h = d2h.ms();
+          }
+          stats[r] = eng.stats;
+        } catch (const std::exception& e) {
+          group->fail("rank " + std::to_string(r) + ": " + e.what());
+        }
+      });
+    }
+    for (std::thread& t : threads) t.join();
+    if (group->failed()) capsb::fail(group->failure());
+    if (stats_out)
+      for (int r = 0; r < num_ranks; ++r) fill_stats(stats[r], stats_out + r);
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+template <class IdxT>
+int construct_sharded_device(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, void* stream) {
+  if (!engine) return bad_args("engine is NULL");
+  if (n > 0 && !d_text) return bad_args("NULL buffer");
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
+  if (!engine->impl.comm) return bad_args("the engine has not joined a communicator (caps_sa_gpu_engine_comm_init)");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    capsb::StreamScope scope(eng, stream ? static_cast<cudaStream_t>(stream) : eng.stream);
+    capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, static_cast<const uint8_t*>(d_text), n, shard_of<IdxT>(eng));
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+template <class IdxT>
+int construct_sharded_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, IdxT* sa_out, IdxT* lcp_out) {
+  if (!engine) return bad_args("engine is NULL");
+  if (n > 0 && (!text || !sa_out || !lcp_out)) return bad_args("NULL buffer");
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
+  if (!engine->impl.comm) return bad_args("the engine has not joined a communicator (caps_sa_gpu_engine_comm_init)");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    cudaStream_t st = eng.stream;
+    capsb::ShardResult<IdxT>& shard = shard_of<IdxT>(eng);
+    float ms_h2d = 0;
+    {
+      capsb::DevBuf<uint8_t> d_text(n, st);
+      EventPair h2d;
+      CAPSB_CUDA(cudaEventRecord(h2d.a, st));
+      CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
+      CAPSB_CUDA(cudaEventRecord(h2d.b, st));
+      capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, d_text.get(), n, shard);
+      ms_h2d = h2d.ms();
+    }
+    EventPair d2h;
+    CAPSB_CUDA(cudaEventRecord(d2h.a, st));
+    if (shard.count) {
+      CAPSB_CUDA(cudaMemcpyAsync(sa_out + shard.offset, shard.sa.get(), shard.count * sizeof(IdxT),
+                                 cudaMemcpyDeviceToHost, st));
+      CAPSB_CUDA(cudaMemcpyAsync(lcp_out + shard.offset, shard.lcp.get(), shard.count * sizeof(IdxT),
+                                 cudaMemcpyDeviceToHost, st));
+    }
+    CAPSB_CUDA(cudaEventRecord(d2h.b, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    eng.stats.ms_h2d = ms_h2d;
+    eng.stats.ms_d2h = d2h.ms();
+    return CAPS_SA_GPU_OK;
+  });
+}
+
 }  // namespace
 
 extern "C" {
@@ -138,22 +290,7 @@ void caps_sa_gpu_engine_destroy(caps_sa_gpu_engine* engine) { delete engine; }
 
 int caps_sa_gpu_engine_stats(const caps_sa_gpu_engine* engine, caps_sa_gpu_stats* out) {
   if (!engine || !out) return bad_args("NULL argument");
-  const capsb::Stats& s = engine->impl.stats;
-  out->n = s.n;
-  out->idx_bytes = s.idx_bytes;
-  out->bits_per_symbol = s.bits_per_symbol;
-  out->alphabet_size = s.alphabet_size;
-  out->refine_rounds = s.refine_rounds;
-  out->tied_after_key_sort = s.tied_after_key_sort;
-  out->deep_lcp_direct = s.deep_lcp_direct;
-  out->deep_lcp_long = s.deep_lcp_long;
-  out->kernel_launches = s.kernel_launches;
-  out->ms_pack = s.ms_pack, out->ms_sort = s.ms_sort, out->ms_heads = s.ms_heads;
-  out->ms_refine = s.ms_refine, out->ms_deep_lcp = s.ms_deep_lcp, out->ms_total = s.ms_total;
-  out->ms_h2d = s.ms_h2d, out->ms_d2h = s.ms_d2h;
-  out->scatter_launches = s.scatter_launches;
-  out->ms_scatter = s.ms_scatter;
-  out->scatter_bytes = s.scatter_bytes;
+  fill_stats(engine->impl.stats, out);
   return CAPS_SA_GPU_OK;
 }
 
@@ -184,6 +321,75 @@ int caps_sa_gpu_construct_device_u32(caps_sa_gpu_engine* engine, const void* d_t
 int caps_sa_gpu_construct_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, uint64_t* d_sa,
                                      uint64_t* d_lcp, void* stream) {
   return construct_device<uint64_t>(engine, d_text, n, d_sa, d_lcp, stream);
+}
+
+int caps_sa_gpu_construct_multi_u32(const int* devices, int num_ranks, const char* text, uint64_t n, uint32_t* sa_out,
+                                    uint32_t* lcp_out, uint64_t /*subproblem_count*/, uint64_t max_context,
+                                    caps_sa_gpu_stats* stats_out) {
+  return construct_multi<uint32_t>(devices, num_ranks, text, n, sa_out, lcp_out, max_context, stats_out);
+}
+int caps_sa_gpu_construct_multi_u64(const int* devices, int num_ranks, const char* text, uint64_t n, uint64_t* sa_out,
+                                    uint64_t* lcp_out, uint64_t /*subproblem_count*/, uint64_t max_context,
+                                    caps_sa_gpu_stats* stats_out) {
+  return construct_multi<uint64_t>(devices, num_ranks, text, n, sa_out, lcp_out, max_context, stats_out);
+}
+
+int caps_sa_gpu_comm_unique_id(void* id_out) {
+  if (!id_out) return bad_args("NULL argument");
+  return guarded([&]() -> int {
+    capsb::nccl_unique_id(id_out);
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+int caps_sa_gpu_engine_comm_init(caps_sa_gpu_engine* engine, const void* id, int rank, int world) {
+  if (!engine || !id) return bad_args("NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return bad_args("bad rank / world size");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    eng.comm.reset();
+    if (world == 1)
+      eng.comm.reset(new capsb::SelfComm());
+    else
+      eng.comm.reset(new capsb::NcclComm(id, rank, world, eng.dev.device));
+    return CAPS_SA_GPU_OK;
+  });
+}
+
+int caps_sa_gpu_construct_sharded_device_u32(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, void* stream) {
+  return construct_sharded_device<uint32_t>(engine, d_text, n, stream);
+}
+int caps_sa_gpu_construct_sharded_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n, void* stream) {
+  return construct_sharded_device<uint64_t>(engine, d_text, n, stream);
+}
+int caps_sa_gpu_construct_sharded_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n, uint32_t* sa_out,
+                                      uint32_t* lcp_out) {
+  return construct_sharded_host<uint32_t>(engine, text, n, sa_out, lcp_out);
+}
+int caps_sa_gpu_construct_sharded_u64(caps_sa_gpu_engine* engine, const char* text, uint64_t n, uint64_t* sa_out,
+                                      uint64_t* lcp_out) {
+  return construct_sharded_host<uint64_t>(engine, text, n, sa_out, lcp_out);
+}
+
+int caps_sa_gpu_shard_copy(caps_sa_gpu_engine* engine, void* sa_dst, void* lcp_dst, int to_host) {
+  if (!engine) return bad_args("engine is NULL");
+  return guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    const bool wide = eng.stats.idx_bytes == 8;
+    const uint64_t count = wide ? eng.shard64.count : eng.shard32.count;
+    const size_t bytes = count * (wide ? 8 : 4);
+    const void* sa = wide ? static_cast<const void*>(eng.shard64.sa.get()) : eng.shard32.sa.get();
+    const void* lcp = wide ? static_cast<const void*>(eng.shard64.lcp.get()) : eng.shard32.lcp.get();
+    if (bytes && (!sa_dst || !lcp_dst)) capsb::fail("NULL destination");
+    if (bytes) {
+      CAPSB_CUDA(cudaMemcpyAsync(sa_dst, sa, bytes, kind, eng.stream));
+      CAPSB_CUDA(cudaMemcpyAsync(lcp_dst, lcp, bytes, kind, eng.stream));
+    }
+    CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+    return CAPS_SA_GPU_OK;
+  });
 }
 
 int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n) {

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 #include "common.cuh"
@@ -26,6 +27,13 @@ struct Stats {
   uint32_t scatter_launches = 0;
   float ms_scatter = 0;
   uint64_t scatter_bytes = 0;
+  uint32_t key_bits = 0;  // leading bits of the packed prefix the key sort used
+  // sharded construction only
+  float ms_partition = 0;     // pivots, pivot location and the (key, suffix) all-to-all
+  float ms_merge = 0;         // merge-path tree over the received runs
+  uint64_t comm_bytes = 0;    // bytes this rank moved to other ranks
+  uint64_t shard_offset = 0;  // this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count)
+  uint64_t shard_count = 0;
 };
 
 struct PackedTextBuf {
@@ -34,6 +42,15 @@ struct PackedTextBuf {
   unsigned log2_bits = 3;
   unsigned sigma = 0;
   PackedText view(uint64_t n) const { return PackedText{words.get(), n, log2_bits}; }
+};
+
+struct Comm;  // comm.cuh
+
+// Result of a sharded construction on one rank: entries [offset, offset + count) of SA and LCP.
+template <class IdxT>
+struct ShardResult {
+  DevBuf<IdxT> sa, lcp;
+  uint64_t offset = 0, count = 0;
 };
 
 struct Engine {
@@ -45,6 +62,10 @@ struct Engine {
   ScanScratch<uint64_t> scan64;
   Stats stats;
   std::vector<cudaEvent_t> events;
+  // sharded construction (multi-process): the transport this engine joined and its last shard
+  std::unique_ptr<Comm> comm;
+  ShardResult<uint32_t> shard32;
+  ShardResult<uint64_t> shard64;
 
   explicit Engine(int device);
   ~Engine();
@@ -75,6 +96,10 @@ void map_acgt_device(Engine& eng, uint8_t* d_text, uint64_t n);
 // sa_build.cu — the construction path (reference construct(), src/Suffix_Array.cpp:466-494)
 template <class IdxT>
 void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, IdxT* d_lcp);
+
+// sharded_build.cu — the same path with one rank per GPU; collective over the ranks of `comm`
+template <class IdxT>
+void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64_t n, ShardResult<IdxT>& out);
 
 // Test hook: the two scan flavours the pipeline uses (inclusive max, exclusive sum).
 void stage_scan_u32(Engine& eng, const uint32_t* d_in, uint32_t* d_out, uint64_t n, bool inclusive_max);

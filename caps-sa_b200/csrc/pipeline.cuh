@@ -1,0 +1,451 @@
+// Building blocks shared by the single-GPU construction (sa_build.cu) and the sharded one
+// (sharded_build.cu):
+//   sort_suffix_slice   stable LSD radix sort of a slice of suffixes on their packed-prefix key
+//                       (replaces permute + sort_subarrays/merge_sort, reference
+//                       src/Suffix_Array.cpp:112-184);
+//   refine_tied_groups  prefix-doubling rank refinement restricted to the suffixes that are
+//                       still tied (replaces the character compares inside merge, :69-80);
+//                       where the ranks live is a policy: one array (LocalRanks) or sharded by
+//                       text position with an exchange per round (ShardedRanks);
+//   key_lcp             LCP of neighbours with different keys: clz(key_a ^ key_b);
+//   plcp_for_pairs      LCP of tied neighbours by the permuted-LCP recurrence
+//                       PLCP[i] = PLCP[i-1] - 1 on reducible positions and a packed-word
+//                       comparison on the irreducible ones (replaces the LCPs carried
+//                       through merge, :61-68,:78).
+#pragma once
+
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "engine.cuh"
+
+namespace capsb {
+
+template <class IdxT>
+struct IdxTraits;
+template <>
+struct IdxTraits<uint32_t> {
+  using Comp = uint64_t;  // (group head + in-range bit) << 32 | second rank
+  static constexpr unsigned kField = 32;
+};
+template <>
+struct IdxTraits<uint64_t> {
+  using Comp = unsigned __int128;
+  static constexpr unsigned kField = 64;
+};
+
+inline unsigned bit_length(uint64_t v) {
+  unsigned b = 0;
+  while (v) ++b, v >>= 1;
+  return b ? b : 1;
+}
+inline unsigned round_up8(unsigned b) { return (b + 7u) & ~7u; }
+
+// Width of the sort key.  Every 8 bits cost one radix pass over all n suffixes (24 B/suffix of
+// HBM traffic with 32-bit indices), while a suffix left tied costs a few hundred bytes in the
+// refinement; log2(n) + 8 bits leave about n/512 accidental ties on random text, so the key
+// stops there instead of always spending all 64 bits.  A multiple of 8 is a whole number of
+// symbols for every code width (1, 2, 4, 8 bits).
+inline unsigned choose_key_bits(uint64_t n) {
+  unsigned bits = round_up8(bit_length(n) + 8);
+  if (const char* env = std::getenv("CAPSB_KEY_BITS")) bits = round_up8(static_cast<unsigned>(std::atoi(env)));
+  return bits < 16 ? 16 : (bits > 64 ? 64 : bits);
+}
+inline uint64_t key_mask_of(unsigned key_bits) { return key_bits >= 64 ? ~0ull : ~0ull << (64 - key_bits); }
+
+// First radix pass reads keys from the packed text: key = window at suffix base + i (leading
+// key bits only), value = base + i.
+template <class IdxT>
+struct TextSource {
+  PackedText pt;
+  uint64_t mask;
+  uint64_t base;
+  __device__ __forceinline__ uint64_t key(uint64_t i) const { return pt.window(base + i) & mask; }
+  __device__ __forceinline__ IdxT val(uint64_t i) const { return static_cast<IdxT>(base + i); }
+  // the text window is re-read from L1/L2; compulsory traffic is the packed text itself (< 1 B)
+  static constexpr uint64_t bytes_read_per_item() { return 1; }
+};
+
+// Stage timer: records an event now; elapsed times are read at the end.
+struct StageClock {
+  Engine& eng;
+  std::vector<cudaEvent_t> marks;
+  explicit StageClock(Engine& e) : eng(e) {}
+  void mark() {
+    cudaEvent_t ev;
+    if (!eng.events.empty()) {
+      ev = eng.events.back();
+      eng.events.pop_back();
+    } else {
+      CAPSB_CUDA(cudaEventCreate(&ev));
+    }
+    CAPSB_CUDA(cudaEventRecord(ev, eng.stream));
+    marks.push_back(ev);
+  }
+  float between(size_t a, size_t b) {
+    float ms = 0;
+    CAPSB_CUDA(cudaEventElapsedTime(&ms, marks[a], marks[b]));
+    return ms;
+  }
+  ~StageClock() {
+    for (cudaEvent_t e : marks) eng.events.push_back(e);
+  }
+};
+
+// Scan in two steps so the total (a count) is known before the outputs are allocated.
+template <class T, class Op, class In>
+T scan_total(Engine& eng, uint64_t n, In in) {
+  ScanScratch<T>& sc = eng.scan_scratch<T>();
+  if (n == 0) return Op::template identity<T>();
+  const Chunking ck = make_chunking(n, kScanTile, sc.max_blocks);
+  CAPSB_LAUNCH((scan_reduce_kernel<T, Op, In>), ck.blocks, kScanThreads, 0, eng.stream, n, ck.chunk, in,
+               sc.partial.get());
+  CAPSB_LAUNCH((scan_spine_kernel<T, Op>), 1, kScanThreads, 0, eng.stream, ck.blocks, sc.partial.get(),
+               sc.total.get());
+  T total;
+  CAPSB_CUDA(cudaMemcpyAsync(&total, sc.total.get(), sizeof(T), cudaMemcpyDeviceToHost, eng.stream));
+  CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+  return total;
+}
+// Must directly follow scan_total / another scan of the same n (reuses the partials).
+template <class T, class Op, bool Inclusive, class In, class Out>
+void scan_finish(Engine& eng, uint64_t n, In in, Out out) {
+  ScanScratch<T>& sc = eng.scan_scratch<T>();
+  if (n == 0) return;
+  const Chunking ck = make_chunking(n, kScanTile, sc.max_blocks);
+  CAPSB_LAUNCH((scan_apply_kernel<T, Op, Inclusive, In, Out>), ck.blocks, kScanThreads, 0, eng.stream, n,
+               ck.chunk, in, out, sc.partial.get());
+}
+template <class T, class Op, bool Inclusive, class In, class Out>
+void scan_full(Engine& eng, uint64_t n, In in, Out out) {
+  device_scan<T, Op, Inclusive>(eng.dev, eng.stream, eng.scan_scratch<T>(), n, in, out);
+}
+
+// ---------------------------------------------------------------------------------------
+// Key sort of the suffixes [base, base + count): on return keys_out / sa_out hold them in key
+// order (keys masked to key_bits).  keys_out and sa_out are caller-owned, `count` entries.
+// ---------------------------------------------------------------------------------------
+template <class IdxT>
+void sort_suffix_slice(Engine& eng, const PackedText& pt, uint64_t base, uint64_t count, unsigned key_bits,
+                       uint64_t* keys_out, IdxT* sa_out) {
+  if (count == 0) return;
+  cudaStream_t st = eng.stream;
+  const unsigned passes = key_bits / 8;
+  DevBuf<uint64_t> key_tmp(count, st);
+  DevBuf<IdxT> val_tmp(count, st);
+  // pass q writes buffer pair q & 1; the last pass must leave its output in the caller's arrays
+  const unsigned last = (passes - 1) & 1u;
+  uint64_t* key_buf[2];
+  IdxT* val_buf[2];
+  key_buf[last] = keys_out, val_buf[last] = sa_out;
+  key_buf[last ^ 1u] = key_tmp.get(), val_buf[last ^ 1u] = val_tmp.get();
+  radix_pass<uint64_t, IdxT>(st, eng.radix, TextSource<IdxT>{pt, key_mask_of(key_bits), base}, count, 64 - key_bits,
+                             key_buf[0], val_buf[0]);
+  for (unsigned q = 1; q < passes; ++q) {
+    const unsigned in = (q - 1) & 1u, out = q & 1u;
+    radix_pass<uint64_t, IdxT>(st, eng.radix, ArraySource<uint64_t, IdxT>{key_buf[in], val_buf[in]}, count,
+                               64 - key_bits + 8 * q, key_buf[out], val_buf[out]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Rank storage of the single-GPU path: one array isa[text position] = first SA position of the
+// suffix's current group.
+// ---------------------------------------------------------------------------------------
+template <class IdxT>
+struct LocalRanks {
+  using Comp = typename IdxTraits<IdxT>::Comp;
+  Engine& eng;
+  uint64_t n;
+  DevBuf<IdxT> isa;
+  LocalRanks(Engine& e, uint64_t n_) : eng(e), n(n_), isa(n_, e.stream) {}
+
+  bool any_active(uint64_t m) { return m > 0; }
+
+  // isa[idx[t]] = head[t] for t in [0, m)
+  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
+    IdxT* d_isa = isa.get();
+    launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) { d_isa[idx[t]] = head[t]; });
+  }
+
+  // comp[t] = (group[t] + inside) << field | second, where second is the rank of suffix
+  // idx[t] + h, or n - 1 - idx[t] beyond the end (shorter suffix first = larger position first)
+  void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
+    constexpr unsigned kField = IdxTraits<IdxT>::kField;
+    const IdxT* d_isa = isa.get();
+    const uint64_t n_ = n;
+    launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) {
+      const uint64_t i = idx[t];
+      const uint64_t ih = i + h;
+      const bool inside = ih < n_;
+      const uint64_t second = inside ? static_cast<uint64_t>(d_isa[ih]) : (n_ - 1 - i);
+      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
+                static_cast<Comp>(second);
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// Prefix-doubling refinement.  d_sa[0..count) holds suffixes in key order (SA positions
+// pos_base .. pos_base + count of the final array); keys[] are their (masked) keys, which
+// order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
+// keys must be complete inside [0, count).
+// ---------------------------------------------------------------------------------------
+template <class IdxT, class Ranks>
+void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d_sa, uint64_t count,
+                        uint64_t pos_base, uint64_t n, uint64_t h0) {
+  using Comp = typename IdxTraits<IdxT>::Comp;
+  constexpr unsigned kField = IdxTraits<IdxT>::kField;
+  cudaStream_t st = eng.stream;
+  const DeviceInfo& dev = eng.dev;
+
+  DevBuf<IdxT> group_of(count, st);  // local SA position -> global SA position of its group's head
+  IdxT* d_group = group_of.get();
+  scan_full<IdxT, OpMax, true>(
+      eng, count,
+      [=] __device__(uint64_t k) -> IdxT {
+        return (k == 0 || keys[k] != keys[k - 1]) ? static_cast<IdxT>(pos_base + k) : IdxT(0);
+      },
+      [=] __device__(uint64_t k, IdxT head) { d_group[k] = head; });
+  ranks.publish(d_sa, d_group, count);
+
+  auto in_group = [=] __device__(uint64_t k) -> IdxT {
+    const bool single = d_group[k] == pos_base + k && (k + 1 == count || d_group[k + 1] == pos_base + k + 1);
+    return single ? IdxT(0) : IdxT(1);
+  };
+  uint64_t m = scan_total<IdxT, OpSum>(eng, count, in_group);
+  DevBuf<IdxT> a_pos(m, st), a_idx(m, st), a_group(m, st);
+  {
+    IdxT* p = a_pos.get();
+    IdxT* s = a_idx.get();
+    IdxT* g = a_group.get();
+    scan_finish<IdxT, OpSum, false>(eng, count, in_group, [=] __device__(uint64_t k, IdxT slot) {
+      const bool single = d_group[k] == pos_base + k && (k + 1 == count || d_group[k + 1] == pos_base + k + 1);
+      if (!single) {
+        p[slot] = static_cast<IdxT>(k);
+        s[slot] = d_sa[k];
+        g[slot] = d_group[k];
+      }
+    });
+  }
+  group_of.release();
+
+  const unsigned rank_bits = round_up8(bit_length(n - 1));
+  uint64_t h = h0;
+  static const bool trace = std::getenv("CAPSB_TRACE") != nullptr;  // per-round log on stderr
+  std::chrono::steady_clock::time_point round_start;
+  if (trace) {
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    std::fprintf(stderr, "[capsb] refine: count=%llu active=%llu h0=%llu\n", (unsigned long long)count,
+                 (unsigned long long)m, (unsigned long long)h0);
+  }
+  while (ranks.any_active(m)) {
+    eng.stats.refine_rounds++;
+    if (trace) round_start = std::chrono::steady_clock::now();
+    DevBuf<Comp> comp_a(m, st), comp_b(m, st);
+    DevBuf<IdxT> idx_b(m, st), head_slot(m, st);
+    ranks.make_comp(a_idx.get(), a_group.get(), m, h, comp_a.get());
+
+    // sort by (group, second rank): LSD over the second-rank field, then the group field
+    Comp* kin = comp_a.get();
+    IdxT* vin = a_idx.get();
+    Comp* kout = comp_b.get();
+    IdxT* vout = idx_b.get();
+    for (unsigned field = 0; field < 2; ++field)
+      for (unsigned shift = field * kField; shift < field * kField + rank_bits; shift += 8) {
+        radix_pass<Comp, IdxT>(st, eng.radix, ArraySource<Comp, IdxT>{kin, vin}, m, shift, kout, vout);
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+      }
+    const Comp* sorted_comp = kin;
+    const IdxT* sorted_idx = vin;
+
+    IdxT* hs = head_slot.get();
+    scan_full<IdxT, OpMax, true>(
+        eng, m,
+        [=] __device__(uint64_t t) -> IdxT {
+          return (t > 0 && sorted_comp[t] != sorted_comp[t - 1]) ? static_cast<IdxT>(t) : IdxT(0);
+        },
+        [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
+
+    DevBuf<IdxT> new_group(m, st);
+    {
+      const IdxT* p = a_pos.get();
+      IdxT* ng = new_group.get();
+      launch_map(dev, st, m, [=] __device__(uint64_t t) {
+        d_sa[p[t]] = sorted_idx[t];
+        ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
+      });
+    }
+    ranks.publish(sorted_idx, new_group.get(), m);
+
+    auto still_tied = [=] __device__(uint64_t t) -> IdxT {
+      const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
+      return single ? IdxT(0) : IdxT(1);
+    };
+    const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
+    DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
+    if (m_next > 0) {
+      const IdxT* p = a_pos.get();
+      const IdxT* ng = new_group.get();
+      IdxT* np = n_pos.get();
+      IdxT* ns = n_idx.get();
+      IdxT* ngp = n_group.get();
+      scan_finish<IdxT, OpSum, false>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
+        const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
+        if (!single) {
+          np[slot] = p[t];
+          ns[slot] = sorted_idx[t];
+          ngp[slot] = ng[t];
+        }
+      });
+    }
+    a_pos = std::move(n_pos);
+    a_idx = std::move(n_idx);
+    a_group = std::move(n_group);
+    if (trace) {
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
+      std::fprintf(stderr, "[capsb] refine round %u: h=%llu active=%llu -> %llu  %.3f ms\n", eng.stats.refine_rounds,
+                   (unsigned long long)h, (unsigned long long)m, (unsigned long long)m_next, ms);
+    }
+    m = m_next;
+    if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
+    h <<= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// LCP of neighbours with different keys comes from the keys alone: clz(key_a ^ key_b) / bits,
+// bounded by the shorter suffix.  It needs the FINAL predecessor (the bound depends on which
+// member of the previous group ends up last), so it runs after the refinement.  The
+// predecessor of local position 0 is (prev_key, prev_idx) when has_prev, else LCP is 0.
+// ---------------------------------------------------------------------------------------
+template <class IdxT>
+void key_lcp(Engine& eng, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t n,
+             unsigned log2_bits, bool has_prev, uint64_t prev_key, uint64_t prev_idx) {
+  launch_map(eng.dev, eng.stream, count, [=] __device__(uint64_t k) {
+    uint64_t pk, a;
+    if (k == 0) {
+      if (!has_prev) {
+        d_lcp[0] = 0;
+        return;
+      }
+      pk = prev_key, a = prev_idx;
+    } else {
+      pk = keys[k - 1], a = d_sa[k - 1];
+    }
+    const uint64_t x = keys[k] ^ pk;
+    if (x != 0) {
+      const uint64_t b = d_sa[k];
+      const uint64_t shorter = n - (a > b ? a : b);
+      const uint64_t l = static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> log2_bits;
+      d_lcp[k] = static_cast<IdxT>(l < shorter ? l : shorter);
+    }
+  });
+}
+
+// Block-wide comparison for the few very long common prefixes (one CTA per pair).
+template <class IdxT, class PosJ>
+__global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const uint64_t* __restrict__ pos_i, PosJ pos_j,
+                                                       const IdxT* __restrict__ todo, uint64_t todo_count,
+                                                       IdxT* __restrict__ plcp) {
+  __shared__ unsigned long long best;
+  constexpr int kPerThread = 4;
+  const unsigned spw = pt.syms_per_word();
+  for (uint64_t e = blockIdx.x; e < todo_count; e += gridDim.x) {
+    const uint64_t t = todo[e];
+    const uint64_t i = pos_i[t], j = pos_j(t);
+    const uint64_t shorter = pt.n - (i > j ? i : j);
+    uint64_t base = plcp[t];  // symbols already known equal (multiple of spw)
+    while (true) {
+      if (threadIdx.x == 0) best = ~0ull;
+      __syncthreads();
+      unsigned long long mine = ~0ull;
+#pragma unroll
+      for (int q = 0; q < kPerThread; ++q) {
+        const uint64_t off = base + (static_cast<uint64_t>(q) * 256 + threadIdx.x) * spw;
+        if (off >= shorter) {
+          if (shorter < mine) mine = shorter;
+        } else {
+          const uint64_t x = pt.window(i + off) ^ pt.window(j + off);
+          if (x != 0) {
+            const uint64_t l = off + (static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> pt.log2_bits);
+            if (l < mine) mine = l;
+          }
+        }
+      }
+      if (mine != ~0ull) atomicMin(&best, mine);
+      __syncthreads();
+      const unsigned long long got = best;
+      __syncthreads();
+      if (got != ~0ull) {
+        if (threadIdx.x == 0) plcp[t] = static_cast<IdxT>(got < shorter ? got : shorter);
+        break;
+      }
+      base += static_cast<uint64_t>(kPerThread) * 256 * spw;
+    }
+  }
+}
+
+// LCPs of m suffix pairs (i_t, j_t), given in increasing order of i_t (pos_i) with j_t =
+// pos_j(t) the suffix that precedes i_t in the suffix array.  Pair t is reducible when the
+// pair (i_t - 1, j_t - 1) is pair t-1 of the list and the preceding symbols agree; then
+// LCP_t = LCP_{t-1} - 1 (Karkkainen-Manzini-Puglisi).  Irreducible pairs are compared
+// directly: 16 packed words per thread, then one CTA per pair for the rare long ones.
+// out(t, lcp) is called once per pair.
+template <class IdxT, class PosJ, class Out>
+void plcp_for_pairs(Engine& eng, const PackedText& pt, const uint64_t* pos_i, PosJ pos_j, uint64_t m, Out out) {
+  if (m == 0) return;
+  cudaStream_t st = eng.stream;
+  const DeviceInfo& dev = eng.dev;
+  DevBuf<IdxT> plcp(m, st), todo(m, st), chain_head(m, st);
+  DevBuf<unsigned long long> counters(2, st);
+  CAPSB_CUDA(cudaMemsetAsync(counters.get(), 0, 2 * sizeof(unsigned long long), st));
+  {
+    IdxT* pl = plcp.get();
+    IdxT* td = todo.get();
+    IdxT* ch = chain_head.get();
+    unsigned long long* cnt = counters.get();
+    launch_map(dev, st, m, [=] __device__(uint64_t t) {
+      const uint64_t i = pos_i[t];
+      const uint64_t j = pos_j(t);
+      // reducible: the pair (i-1, j-1) precedes it in the list (then it IS the list's previous
+      // pair) and the preceding symbols agree
+      const bool chained =
+          t > 0 && pos_i[t - 1] + 1 == i && i > 0 && j > 0 && pt.symbol(i - 1) == pt.symbol(j - 1);
+      ch[t] = chained ? IdxT(0) : static_cast<IdxT>(t);
+      if (!chained) {
+        uint64_t l = 0;
+        const bool done = pt.common_prefix(i, j, 0, 16, &l);
+        pl[t] = static_cast<IdxT>(l);
+        atomicAdd(cnt + 0, 1ull);
+        if (!done) td[atomicAdd(cnt + 1, 1ull)] = static_cast<IdxT>(t);
+      }
+    });
+  }
+  unsigned long long h_cnt[2];
+  CAPSB_CUDA(cudaMemcpyAsync(h_cnt, counters.get(), sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+  eng.stats.deep_lcp_direct += h_cnt[0];
+  eng.stats.deep_lcp_long += h_cnt[1];
+  if (h_cnt[1] > 0) {
+    const unsigned grid =
+        static_cast<unsigned>(std::min<uint64_t>(h_cnt[1], static_cast<uint64_t>(dev.sm_count) * 8));
+    CAPSB_LAUNCH((long_lcp_kernel<IdxT, PosJ>), grid, 256, 0, st, pt, pos_i, pos_j, todo.get(),
+                 static_cast<uint64_t>(h_cnt[1]), plcp.get());
+  }
+  {
+    const IdxT* pl = plcp.get();
+    const IdxT* ch = chain_head.get();
+    scan_full<IdxT, OpMax, true>(
+        eng, m, [=] __device__(uint64_t t) -> IdxT { return ch[t]; },
+        [=] __device__(uint64_t t, IdxT head) {
+          const uint64_t back = pos_i[t] - pos_i[head];
+          out(t, static_cast<IdxT>(static_cast<uint64_t>(pl[head]) - back));
+        });
+  }
+}
+
+}  // namespace capsb

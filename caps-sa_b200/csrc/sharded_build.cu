@@ -1,0 +1,453 @@
+// Sharded (multi-GPU) suffix-array + LCP construction: the samplesort shape of the reference
+// (src/Suffix_Array.cpp:466-494) with one rank per GPU.
+//
+//   text              replicated: every rank stages and packs the whole text in its HBM
+//   sort_subarrays    (:161-184)  rank r key-sorts the suffixes that start in its slice of the
+//                                 text (last slice takes the remainder, as :172)
+//   select_pivots     (:197-222)  regular samples of every sorted slice, all-gathered; every
+//                                 rank sorts the same sample set and picks the same G-1 pivots
+//   locate_pivots     (:225-249)  warp-cooperative upper-bound search of each pivot in the
+//                                 sorted slice -> send counts; all-gather -> the G x G matrix P
+//   partition/collate (:300-368)  variable all-to-all of (key, suffix) runs over NVLink
+//   merge_sub_subarrays (:371-428) merge-path tree over the G received runs (merge_path.cuh)
+//   ties                          prefix doubling on ranks sharded by text position: one
+//                                 request/response exchange and one update exchange per round
+//   LCP               (:61-68,:78,:431-447) neighbours with different keys: from the keys (the
+//                                 predecessor of a bucket's first suffix comes from the
+//                                 previous rank = the reference's boundary patch); tied
+//                                 neighbours travel to the rank that owns their text position,
+//                                 where the permuted-LCP chains are contiguous, and back.
+// Pivots are keys, so suffixes with equal keys land on one rank and tie groups never span
+// ranks; rank r ends up owning the contiguous range [offset, offset + count) of SA and LCP.
+#include "comm.cuh"
+#include "merge_path.cuh"
+#include "pipeline.cuh"
+
+namespace capsb {
+
+namespace {
+
+// Slices of text positions: rank r owns [r * slice, (r + 1) * slice), the last rank to n.
+struct SliceMap {
+  uint64_t n;
+  uint64_t slice;
+  unsigned world;
+  __host__ __device__ unsigned owner(uint64_t pos) const {
+    if (slice == 0) return world - 1;
+    const uint64_t o = pos / slice;
+    return o < world - 1 ? static_cast<unsigned>(o) : world - 1;
+  }
+  __host__ __device__ uint64_t begin(unsigned r) const { return static_cast<uint64_t>(r) * slice; }
+  __host__ __device__ uint64_t end(unsigned r) const {
+    return r + 1 == world ? n : static_cast<uint64_t>(r + 1) * slice;
+  }
+};
+
+template <class IdxT>
+struct IdxPair {
+  IdxT a, b;
+};
+
+// ---- routing items to owner ranks ------------------------------------------------------
+// A route is a stable partition of m local items by destination rank (one counting pass of
+// the radix machinery on the destination as an 8-bit digit) plus the exchanged counts.
+template <class IdxT>
+struct Route {
+  uint64_t m = 0;
+  uint64_t recv_total = 0;
+  DevBuf<IdxT> perm;  // perm[j] = local item that travels in position j
+  std::vector<uint64_t> send_counts, recv_counts;
+};
+
+template <class IdxT, class DestFn>
+struct DestSource {
+  DestFn dest;
+  __device__ __forceinline__ uint8_t key(uint64_t t) const { return static_cast<uint8_t>(dest(t)); }
+  __device__ __forceinline__ IdxT val(uint64_t t) const { return static_cast<IdxT>(t); }
+  static constexpr uint64_t bytes_read_per_item() { return sizeof(IdxT); }
+};
+
+template <class IdxT, class DestFn>
+Route<IdxT> plan_route(Engine& eng, Comm& comm, uint64_t m, DestFn dest) {
+  cudaStream_t st = eng.stream;
+  const unsigned world = static_cast<unsigned>(comm.world);
+  if (world > static_cast<unsigned>(kRadixSize)) fail("more ranks than the routing digit can hold");
+  Route<IdxT> r;
+  r.m = m;
+  r.send_counts.assign(world, 0);
+  r.recv_counts.assign(world, 0);
+  if (m) {
+    r.perm.alloc(m, st);
+    DevBuf<uint8_t> sorted_dest(m, st);
+    radix_pass<uint8_t, IdxT>(st, eng.radix, DestSource<IdxT, DestFn>{dest}, m, 0, sorted_dest.get(), r.perm.get());
+    CAPSB_CUDA(cudaMemcpyAsync(r.send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t),
+                               cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+  }
+  std::vector<uint64_t> matrix(static_cast<size_t>(world) * world);
+  comm.all_gather_host(r.send_counts.data(), world * sizeof(uint64_t), matrix.data(), st);
+  for (unsigned s = 0; s < world; ++s) {
+    r.recv_counts[s] = matrix[static_cast<size_t>(s) * world + comm.rank];
+    r.recv_total += r.recv_counts[s];
+  }
+  return r;
+}
+
+// recv[j] (j over the items this rank receives, grouped by source rank) = in(item)
+template <class T, class IdxT, class In>
+void route_forward(Engine& eng, Comm& comm, const Route<IdxT>& r, In in, T* recv) {
+  cudaStream_t st = eng.stream;
+  DevBuf<T> send(r.m, st);
+  {
+    T* s = send.get();
+    const IdxT* perm = r.perm.get();
+    launch_map(eng.dev, st, r.m, [=] __device__(uint64_t j) { s[j] = in(static_cast<uint64_t>(perm[j])); });
+  }
+  comm.all_to_all_v(send.get(), r.send_counts.data(), recv, r.recv_counts.data(), sizeof(T), st);
+}
+
+// The reverse trip: answers[j] for every received item go back to the sender, which gets
+// out(item, answer).
+template <class T, class IdxT, class Out>
+void route_backward(Engine& eng, Comm& comm, const Route<IdxT>& r, const T* answers, Out out) {
+  cudaStream_t st = eng.stream;
+  DevBuf<T> back(r.m, st);
+  comm.all_to_all_v(answers, r.recv_counts.data(), back.get(), r.send_counts.data(), sizeof(T), st);
+  const T* b = back.get();
+  const IdxT* perm = r.perm.get();
+  launch_map(eng.dev, st, r.m, [=] __device__(uint64_t j) { out(static_cast<uint64_t>(perm[j]), b[j]); });
+}
+
+// ---- ranks sharded by text position ----------------------------------------------------
+template <class IdxT>
+struct ShardedRanks {
+  using Comp = typename IdxTraits<IdxT>::Comp;
+  Engine& eng;
+  Comm& comm;
+  SliceMap map;
+  uint64_t lo;              // first text position of this rank's slice
+  DevBuf<IdxT> isa_local;   // isa_local[pos - lo] = first SA position of suffix pos's group
+
+  ShardedRanks(Engine& e, Comm& c, SliceMap m)
+      : eng(e), comm(c), map(m), lo(m.begin(static_cast<unsigned>(c.rank))) {
+    const uint64_t count = m.end(static_cast<unsigned>(c.rank)) - lo;
+    isa_local.alloc(count ? count : 1, e.stream);
+  }
+
+  bool any_active(uint64_t m) {
+    std::vector<uint64_t> all(static_cast<size_t>(comm.world));
+    comm.all_gather_host(&m, sizeof(m), all.data(), eng.stream);
+    for (uint64_t v : all)
+      if (v) return true;
+    return false;
+  }
+
+  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
+    const SliceMap mp = map;
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(idx[t]); });
+    DevBuf<IdxPair<IdxT>> recv(rt.recv_total, eng.stream);
+    route_forward<IdxPair<IdxT>>(
+        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{idx[t], head[t]}; }, recv.get());
+    IdxT* isa = isa_local.get();
+    const IdxPair<IdxT>* rv = recv.get();
+    const uint64_t lo_ = lo;
+    launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { isa[rv[j].a - lo_] = rv[j].b; });
+  }
+
+  void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
+    constexpr unsigned kField = IdxTraits<IdxT>::kField;
+    const SliceMap mp = map;
+    const uint64_t n = map.n, lo_ = lo;
+    const unsigned self = static_cast<unsigned>(comm.rank);
+    // suffixes that run past the end need no rank; they ride along as a request to this rank
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned {
+      const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
+      return ih < n ? mp.owner(ih) : self;
+    });
+    DevBuf<IdxT> asked(rt.recv_total, eng.stream), answers(rt.recv_total, eng.stream);
+    route_forward<IdxT>(
+        eng, comm, rt,
+        [=] __device__(uint64_t t) -> IdxT {
+          const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
+          return static_cast<IdxT>(ih < n ? ih : lo_);
+        },
+        asked.get());
+    {
+      const IdxT* isa = isa_local.get();
+      const IdxT* q = asked.get();
+      IdxT* a = answers.get();
+      launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { a[j] = isa[q[j] - lo_]; });
+    }
+    route_backward<IdxT>(eng, comm, rt, answers.get(), [=] __device__(uint64_t t, IdxT rank_of_ih) {
+      const uint64_t i = idx[t];
+      const bool inside = i + h < n;
+      const uint64_t second = inside ? static_cast<uint64_t>(rank_of_ih) : (n - 1 - i);
+      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
+                static_cast<Comp>(second);
+    });
+  }
+};
+
+// ---- pivot location --------------------------------------------------------------------
+// One warp per pivot: 32-ary upper-bound search in the sorted keys (first position whose key
+// is greater than the pivot).  bounds[0] = 0, bounds[j + 1] = upper_bound(pivot j),
+// bounds[pivots + 1] = count.  Pivot j is sorted_samples[(j + 1) * stride - 1].
+__global__ void __launch_bounds__(256) locate_pivots_kernel(const uint64_t* __restrict__ keys, uint64_t count,
+                                                            const uint64_t* __restrict__ sorted_samples,
+                                                            uint64_t stride, unsigned pivots,
+                                                            uint64_t* __restrict__ bounds) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  if (warp == 0 && lane == 0) {
+    bounds[0] = 0;
+    bounds[pivots + 1] = count;
+  }
+  if (warp >= pivots) return;
+  const uint64_t pivot = sorted_samples[static_cast<uint64_t>(warp + 1) * stride - 1];
+  uint64_t lo = 0, hi = count;  // answer in [lo, hi]
+  while (hi - lo > 32) {
+    const uint64_t width = hi - lo;
+    const uint64_t probe = lo + (static_cast<uint64_t>(lane + 1) * width) / 33;  // strictly inside [lo, hi)
+    const bool le = keys[probe] <= pivot;
+    const unsigned vote = __ballot_sync(0xffffffffu, le);
+    const int c = __popc(vote);  // probes are increasing, so `le` is a prefix of the lanes
+    const uint64_t below = __shfl_sync(0xffffffffu, probe, c > 0 ? c - 1 : 0);
+    const uint64_t above = __shfl_sync(0xffffffffu, probe, c < 32 ? c : 31);
+    if (c > 0) lo = below + 1;
+    if (c < 32) hi = above;
+  }
+  const bool le = lo + lane < hi && keys[lo + lane] <= pivot;
+  const unsigned vote = __ballot_sync(0xffffffffu, le);
+  if (lane == 0) bounds[warp + 1] = lo + static_cast<uint64_t>(__popc(vote));
+}
+
+constexpr unsigned kSamplesPerRank = 1024;
+
+}  // namespace
+
+template <class IdxT>
+void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64_t n, ShardResult<IdxT>& out) {
+  CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+  cudaStream_t st = eng.stream;
+  const DeviceInfo& dev = eng.dev;
+  const unsigned world = static_cast<unsigned>(comm.world);
+  const unsigned rank = static_cast<unsigned>(comm.rank);
+  const uint64_t launches_before = g_kernel_launches.load();
+  const uint64_t comm_bytes_before = comm.bytes_sent;
+  eng.stats = Stats();
+  eng.radix.timer.reset();
+  eng.stats.n = n;
+  eng.stats.idx_bytes = sizeof(IdxT);
+  out.offset = out.count = 0;
+  out.sa.release();
+  out.lcp.release();
+  if (n == 0) return;
+  if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) fail("text too long for 32-bit indices");
+
+  StageClock clock(eng);
+  clock.mark();  // 0
+
+  // ---- text staging + key packing (whole text, every rank) -------------------------------
+  PackedTextBuf packed = pack_text(eng, d_text, n);
+  const PackedText pt = packed.view(n);
+  const unsigned log2_bits = pt.log2_bits;
+  eng.stats.bits_per_symbol = pt.bits();
+  eng.stats.alphabet_size = packed.sigma;
+  clock.mark();  // 1
+
+  // ---- slice sort ------------------------------------------------------------------------
+  const SliceMap map{n, n / world, world};
+  const uint64_t lo = map.begin(rank);
+  const uint64_t slice_count = map.end(rank) - lo;
+  const unsigned key_bits = choose_key_bits(n);
+  eng.stats.key_bits = key_bits;
+  DevBuf<uint64_t> slice_keys(slice_count, st);
+  DevBuf<IdxT> slice_idx(slice_count, st);
+  sort_suffix_slice<IdxT>(eng, pt, lo, slice_count, key_bits, slice_keys.get(), slice_idx.get());
+  clock.mark();  // 2
+
+  // ---- pivots: regular samples, all-gather, every rank sorts the same sample set ----------
+  const uint64_t sample_total = static_cast<uint64_t>(kSamplesPerRank) * world;
+  DevBuf<uint64_t> samples(kSamplesPerRank, st), all_a(sample_total, st), all_b(sample_total, st);
+  DevBuf<uint32_t> dummy_a(sample_total, st), dummy_b(sample_total, st);
+  CAPSB_CUDA(cudaMemsetAsync(dummy_a.get(), 0, sample_total * sizeof(uint32_t), st));
+  {
+    uint64_t* s = samples.get();
+    const uint64_t* k = slice_keys.get();
+    launch_map(dev, st, kSamplesPerRank, [=] __device__(uint64_t t) {
+      // regular sampling (reference sample_pivots, src/Suffix_Array.cpp:187-194); an empty
+      // slice contributes the largest key so it does not pull the pivots down
+      s[t] = slice_count ? k[((t + 1) * slice_count + kSamplesPerRank - 1) / kSamplesPerRank - 1] : ~0ull;
+    });
+  }
+  comm.all_gather_device(samples.get(), all_a.get(), kSamplesPerRank * sizeof(uint64_t), st);
+  const int sorted_in_b = radix_sort_pairs<uint64_t, uint32_t>(st, eng.radix, all_a.get(), dummy_a.get(), all_b.get(),
+                                                              dummy_b.get(), sample_total, 64 - key_bits, 64);
+  const uint64_t* sorted_samples = sorted_in_b ? all_b.get() : all_a.get();
+
+  // ---- locate the pivots in the sorted slice -> send counts -> the G x G count matrix ------
+  DevBuf<uint64_t> d_bounds(world + 1, st);
+  {
+    const unsigned pivots = world - 1;
+    const unsigned blocks = pivots ? static_cast<unsigned>(ceil_div(pivots, 8)) : 1;
+    CAPSB_LAUNCH(locate_pivots_kernel, blocks, 256, 0, st, slice_keys.get(), slice_count, sorted_samples,
+                 static_cast<uint64_t>(kSamplesPerRank), pivots, d_bounds.get());
+  }
+  std::vector<uint64_t> bounds(world + 1);
+  CAPSB_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.get(), (world + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint64_t> send_counts(world), recv_counts(world), matrix(static_cast<size_t>(world) * world);
+  for (unsigned p = 0; p < world; ++p) send_counts[p] = bounds[p + 1] - bounds[p];
+  comm.all_gather_host(send_counts.data(), world * sizeof(uint64_t), matrix.data(), st);
+  uint64_t bucket_count = 0, bucket_offset = 0;
+  for (unsigned s = 0; s < world; ++s) {
+    recv_counts[s] = matrix[static_cast<size_t>(s) * world + rank];
+    bucket_count += recv_counts[s];
+    for (unsigned q = 0; q < rank; ++q) bucket_offset += matrix[static_cast<size_t>(s) * world + q];
+  }
+  out.offset = bucket_offset;
+  out.count = bucket_count;
+  eng.stats.shard_offset = bucket_offset;
+  eng.stats.shard_count = bucket_count;
+
+  // ---- collate: (key, suffix) runs move to the rank that owns their bucket -----------------
+  DevBuf<uint64_t> bucket_keys(bucket_count, st), bucket_keys_tmp(bucket_count, st);
+  DevBuf<IdxT> bucket_idx_tmp(bucket_count, st);
+  out.sa.alloc(bucket_count, st);
+  comm.all_to_all_v(slice_keys.get(), send_counts.data(), bucket_keys.get(), recv_counts.data(), sizeof(uint64_t), st);
+  comm.all_to_all_v(slice_idx.get(), send_counts.data(), out.sa.get(), recv_counts.data(), sizeof(IdxT), st);
+  slice_keys.release();
+  slice_idx.release();
+  clock.mark();  // 3
+
+  // ---- bucket merge ------------------------------------------------------------------------
+  {
+    std::vector<uint64_t> offsets(world + 1, 0);
+    for (unsigned s = 0; s < world; ++s) offsets[s + 1] = offsets[s] + recv_counts[s];
+    const int in_tmp = merge_sorted_runs<uint64_t, IdxT>(dev, st, bucket_keys.get(), out.sa.get(),
+                                                        bucket_keys_tmp.get(), bucket_idx_tmp.get(), offsets);
+    if (in_tmp) {
+      std::swap(bucket_keys, bucket_keys_tmp);
+      std::swap(out.sa, bucket_idx_tmp);
+    }
+  }
+  bucket_keys_tmp.release();
+  bucket_idx_tmp.release();
+  const uint64_t* keys = bucket_keys.get();
+  IdxT* d_sa = out.sa.get();
+  clock.mark();  // 4
+
+  // ---- ties ---------------------------------------------------------------------------------
+  auto tied = [=] __device__(uint64_t k) -> uint64_t { return (k > 0 && keys[k] == keys[k - 1]) ? 1u : 0u; };
+  const uint64_t ties = scan_total<uint64_t, OpSum>(eng, bucket_count, tied);
+  eng.stats.tied_after_key_sort = ties;
+  bool any_ties = false;
+  {
+    std::vector<uint64_t> all(world);
+    comm.all_gather_host(&ties, sizeof(ties), all.data(), st);
+    for (uint64_t v : all) any_ties = any_ties || v > 0;
+  }
+  if (any_ties) {
+    ShardedRanks<IdxT> ranks(eng, comm, map);
+    refine_tied_groups<IdxT>(eng, ranks, keys, d_sa, bucket_count, bucket_offset, n, key_bits >> log2_bits);
+  }
+  clock.mark();  // 5
+
+  // ---- LCP ----------------------------------------------------------------------------------
+  out.lcp.alloc(bucket_count, st);
+  IdxT* d_lcp = out.lcp.get();
+  {
+    // the suffix that precedes this bucket is the last one of the nearest non-empty bucket below
+    struct Edge {
+      uint64_t count, last_key, last_idx;
+    } mine{bucket_count, 0, 0};
+    if (bucket_count) {
+      IdxT last_idx;
+      CAPSB_CUDA(cudaMemcpyAsync(&mine.last_key, keys + bucket_count - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      CAPSB_CUDA(cudaMemcpyAsync(&last_idx, d_sa + bucket_count - 1, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      mine.last_idx = last_idx;
+    }
+    std::vector<Edge> edges(world);
+    comm.all_gather_host(&mine, sizeof(Edge), edges.data(), st);
+    bool has_prev = false;
+    uint64_t prev_key = 0, prev_idx = 0;
+    for (unsigned q = 0; q < rank; ++q)
+      if (edges[q].count) has_prev = true, prev_key = edges[q].last_key, prev_idx = edges[q].last_idx;
+    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, bucket_count, n, log2_bits, has_prev, prev_key, prev_idx);
+  }
+  if (any_ties) {
+    // tied neighbours (always inside one bucket): the pair (i = SA[k], j = SA[k-1]) goes to the
+    // rank that owns text position i
+    DevBuf<IdxT> pair_i(ties, st), pair_j(ties, st), pair_k(ties, st);
+    {
+      IdxT* pi = pair_i.get();
+      IdxT* pj = pair_j.get();
+      IdxT* pk = pair_k.get();
+      scan_full<uint64_t, OpSum, false>(eng, bucket_count, tied, [=] __device__(uint64_t k, uint64_t slot) {
+        if (k > 0 && keys[k] == keys[k - 1]) {
+          pi[slot] = d_sa[k];
+          pj[slot] = d_sa[k - 1];
+          pk[slot] = static_cast<IdxT>(k);
+        }
+      });
+    }
+    const SliceMap mp = map;
+    const IdxT* pi = pair_i.get();
+    const IdxT* pj = pair_j.get();
+    const IdxT* pk = pair_k.get();
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, ties, [=] __device__(uint64_t t) -> unsigned { return mp.owner(pi[t]); });
+    const uint64_t got = rt.recv_total;
+    DevBuf<IdxPair<IdxT>> recv(got, st);
+    route_forward<IdxPair<IdxT>>(
+        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{pi[t], pj[t]}; }, recv.get());
+
+    // order the received pairs by text position so the permuted-LCP chains are contiguous
+    DevBuf<uint64_t> pos_a(got, st), pos_b(got, st);
+    DevBuf<IdxT> slot_a(got, st), slot_b(got, st), answers(got, st);
+    {
+      const IdxPair<IdxT>* rv = recv.get();
+      uint64_t* pa = pos_a.get();
+      IdxT* sa_ = slot_a.get();
+      launch_map(dev, st, got, [=] __device__(uint64_t j) {
+        pa[j] = rv[j].a;
+        sa_[j] = static_cast<IdxT>(j);
+      });
+    }
+    const unsigned pos_bits = round_up8(bit_length(n - 1));
+    const int where = radix_sort_pairs<uint64_t, IdxT>(st, eng.radix, pos_a.get(), slot_a.get(), pos_b.get(),
+                                                      slot_b.get(), got, 0, pos_bits);
+    const uint64_t* pos_i = where ? pos_b.get() : pos_a.get();
+    const IdxT* slot = where ? slot_b.get() : slot_a.get();
+    {
+      const IdxPair<IdxT>* rv = recv.get();
+      IdxT* ans = answers.get();
+      plcp_for_pairs<IdxT>(
+          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return rv[slot[t]].b; }, got,
+          [=] __device__(uint64_t t, IdxT lcp) { ans[slot[t]] = lcp; });
+    }
+    route_backward<IdxT>(eng, comm, rt, answers.get(),
+                         [=] __device__(uint64_t t, IdxT lcp) { d_lcp[pk[t]] = lcp; });
+  }
+  clock.mark();  // 6
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+
+  eng.stats.ms_pack = clock.between(0, 1);
+  eng.stats.ms_sort = clock.between(1, 2);
+  eng.stats.ms_partition = clock.between(2, 3);
+  eng.stats.ms_merge = clock.between(3, 4);
+  eng.stats.ms_refine = clock.between(4, 5);
+  eng.stats.ms_deep_lcp = clock.between(5, 6);
+  eng.stats.ms_total = clock.between(0, 6);
+  eng.stats.comm_bytes = comm.bytes_sent - comm_bytes_before;
+  eng.stats.kernel_launches = g_kernel_launches.load() - launches_before;
+  if (eng.radix.timer.enabled) {
+    eng.stats.scatter_bytes = eng.radix.timer.bytes;
+    eng.stats.ms_scatter = eng.radix.timer.drain(&eng.stats.scatter_launches);
+  }
+}
+
+template void build_sa_lcp_sharded<uint32_t>(Engine&, Comm&, const uint8_t*, uint64_t, ShardResult<uint32_t>&);
+template void build_sa_lcp_sharded<uint64_t>(Engine&, Comm&, const uint8_t*, uint64_t, ShardResult<uint64_t>&);
+
+}  // namespace capsb

@@ -52,6 +52,14 @@ typedef struct caps_sa_gpu_stats {
   uint32_t scatter_launches;
   float ms_scatter;             /* summed duration of those launches */
   uint64_t scatter_bytes;       /* summed algorithmic bytes (keys+values read once, written once) */
+  uint32_t key_bits;            /* leading bits of the packed prefix used as the sort key */
+  uint32_t reserved;
+  /* sharded construction only: */
+  float ms_partition;           /* pivots, pivot location, (key, suffix) all-to-all */
+  float ms_merge;               /* merge-path tree over the received runs */
+  uint64_t comm_bytes;          /* bytes this rank moved to other ranks */
+  uint64_t shard_offset;        /* this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count) */
+  uint64_t shard_count;
 } caps_sa_gpu_stats;
 
 /* Number of CUDA devices visible to the library (0 if none / driver missing). */
@@ -93,6 +101,54 @@ int caps_sa_gpu_construct_device_u32(caps_sa_gpu_engine* engine, const void* d_t
                                      uint32_t* d_sa, uint32_t* d_lcp, void* stream);
 int caps_sa_gpu_construct_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
                                      uint64_t* d_sa, uint64_t* d_lcp, void* stream);
+
+/* ---- Sharded construction: several GPUs, one rank each -------------------------------------
+ * The samplesort shape of the reference (src/Suffix_Array.cpp:466-494) across ranks: the text
+ * is replicated, rank r key-sorts the suffixes of its slice of the text (sort_subarrays,
+ * :161-184), pivots are agreed from all-gathered samples (select_pivots, :197-222), located in
+ * every sorted slice (locate_pivots, :225-249), (key, suffix) runs move to the rank that owns
+ * their bucket in one all-to-all (partition_sub_subarrays, :300-368), each rank merges its
+ * runs (merge_sub_subarrays, :371-428), and the LCP at bucket boundaries comes from the
+ * neighbouring rank (compute_partition_boundary_lcp, :431-447).  Rank r ends up owning the
+ * contiguous range [shard_offset, shard_offset + shard_count) of SA and LCP.
+ *
+ * (1) One process, one host thread per rank (what Suffix_Array<idx_t>::construct() binds when
+ *     CAPS_SA_GPUS > 1).  devices[r] is the CUDA device of rank r; listing a device more than
+ *     once runs several ranks on it (used by the parity tests on a one-GPU box).  Ranks
+ *     exchange data by peer copies (NVLink when the devices differ).  text, sa_out, lcp_out
+ *     are host buffers as in caps_sa_gpu_construct_u32; every rank writes its shard into
+ *     sa_out / lcp_out.  stats_out (may be NULL) receives num_ranks entries. */
+int caps_sa_gpu_construct_multi_u32(const int* devices, int num_ranks, const char* text, uint64_t n,
+                                    uint32_t* sa_out, uint32_t* lcp_out, uint64_t subproblem_count,
+                                    uint64_t max_context, caps_sa_gpu_stats* stats_out);
+int caps_sa_gpu_construct_multi_u64(const int* devices, int num_ranks, const char* text, uint64_t n,
+                                    uint64_t* sa_out, uint64_t* lcp_out, uint64_t subproblem_count,
+                                    uint64_t max_context, caps_sa_gpu_stats* stats_out);
+
+/* (2) One process per GPU (torchrun): the ranks join an NCCL communicator and exchange over
+ *     NVLink / NVSwitch.  Rank 0 creates an id (128 bytes) and the host side broadcasts it (e.g.
+ *     torch.distributed); every rank then calls caps_sa_gpu_engine_comm_init, a collective. */
+#define CAPS_SA_GPU_COMM_ID_BYTES 128
+int caps_sa_gpu_comm_unique_id(void* id_out);
+int caps_sa_gpu_engine_comm_init(caps_sa_gpu_engine* engine, const void* id, int rank, int world);
+
+/* Collective over the engine's communicator.  d_text is this rank's device copy of the whole
+ * text.  The shard stays in device memory owned by the engine until the next construction;
+ * caps_sa_gpu_engine_stats reports shard_offset / shard_count. */
+int caps_sa_gpu_construct_sharded_device_u32(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
+                                             void* stream);
+int caps_sa_gpu_construct_sharded_device_u64(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
+                                             void* stream);
+/* Same with host buffers: stages the text (H2D), constructs, and copies this rank's shard to
+ * sa_out + shard_offset / lcp_out + shard_offset (the arrays have n entries; other ranges are
+ * left untouched). */
+int caps_sa_gpu_construct_sharded_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
+                                      uint32_t* sa_out, uint32_t* lcp_out);
+int caps_sa_gpu_construct_sharded_u64(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
+                                      uint64_t* sa_out, uint64_t* lcp_out);
+/* Copies the last shard (shard_count entries each) to sa_dst / lcp_dst: host memory when
+ * to_host != 0, else device memory on the engine's device. */
+int caps_sa_gpu_shard_copy(caps_sa_gpu_engine* engine, void* sa_dst, void* lcp_dst, int to_host);
 
 /* ---- CLI byte mapping ----------------------------------------------------------------------
  * In-place text[i] = "ACTG"[(toupper(text[i]) & 6) >> 1] for every byte, run on the device

@@ -5,8 +5,11 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <algorithm>
 #include <iostream>
 #include <mutex>
+#include <string>
+#include <vector>
 
 namespace CaPS_SA
 {
@@ -41,6 +44,33 @@ idx_t* pinned_array(std::size_t count)
     if(!p)
         die("Cannot allocate pinned host memory for the suffix array");
     return static_cast<idx_t*>(p);
+}
+
+// Devices of the sharded construction: CAPS_SA_GPUS = a count ("4" -> devices 0..3) or an explicit
+// list ("0,2,3").  Empty / "1" / unset selects the single-device path.
+std::vector<int> sharded_devices()
+{
+    std::vector<int> devices;
+    const char* env = std::getenv("CAPS_SA_GPUS");
+    if(!env || !*env)
+        return devices;
+    const std::string spec(env);
+    if(spec.find(',') == std::string::npos)
+    {
+        const int count = std::atoi(spec.c_str());
+        for(int d = 0; count > 1 && d < count; ++d)
+            devices.push_back(d);
+        return devices;
+    }
+    std::size_t at = 0;
+    while(at <= spec.size())
+    {
+        const std::size_t comma = std::min(spec.find(',', at), spec.size());
+        if(comma > at)
+            devices.push_back(std::atoi(spec.substr(at, comma - at).c_str()));
+        at = comma + 1;
+    }
+    return devices;
 }
 
 inline double seconds_since(const std::chrono::steady_clock::time_point t0)
@@ -84,7 +114,11 @@ template <>
 void Suffix_Array<uint32_t>::construct()
 {
     const auto t0 = std::chrono::steady_clock::now();
-    if(caps_sa_gpu_construct_u32(shared_engine(), T_, n_, SA_, LCP_, subproblem_hint_, max_context_) != CAPS_SA_GPU_OK)
+    const std::vector<int> devices = sharded_devices();
+    const int rc = devices.size() > 1
+        ? caps_sa_gpu_construct_multi_u32(devices.data(), static_cast<int>(devices.size()), T_, n_, SA_, LCP_, subproblem_hint_, max_context_, nullptr)
+        : caps_sa_gpu_construct_u32(shared_engine(), T_, n_, SA_, LCP_, subproblem_hint_, max_context_);
+    if(rc != CAPS_SA_GPU_OK)
         die("Suffix array construction failed");
     constructed_ = true;
     std::cerr << "Constructed the suffix array. Time taken: " << seconds_since(t0) << " seconds.\n";
@@ -95,7 +129,11 @@ template <>
 void Suffix_Array<uint64_t>::construct()
 {
     const auto t0 = std::chrono::steady_clock::now();
-    if(caps_sa_gpu_construct_u64(shared_engine(), T_, n_, SA_, LCP_, subproblem_hint_, max_context_) != CAPS_SA_GPU_OK)
+    const std::vector<int> devices = sharded_devices();
+    const int rc = devices.size() > 1
+        ? caps_sa_gpu_construct_multi_u64(devices.data(), static_cast<int>(devices.size()), T_, n_, SA_, LCP_, subproblem_hint_, max_context_, nullptr)
+        : caps_sa_gpu_construct_u64(shared_engine(), T_, n_, SA_, LCP_, subproblem_hint_, max_context_);
+    if(rc != CAPS_SA_GPU_OK)
         die("Suffix array construction failed");
     constructed_ = true;
     std::cerr << "Constructed the suffix array. Time taken: " << seconds_since(t0) << " seconds.\n";

@@ -126,7 +126,10 @@ def test_golden_dump_digest_simpletest2(pkg, engine, tmp_path):
 
 # ---- whole-path parity: oracle on seeded inputs ---------------------------------------------------
 def oracle_sa_lcp(text, p, idx_bytes=4):
-    if oracle_lib.ref() is not None:
+    # all-equal texts make the reference write one entry past LCP_ (trailing empty partitions,
+    # src/Suffix_Array.cpp:439-440; SURVEY.md §8a hazards): use the restatement there
+    hazardous = len(text) > 0 and bool((text == text[0]).all())
+    if oracle_lib.ref() is not None and not hazardous:
         sa, lcp, _ = oracle_lib.ref_sa_lcp(text, subproblems=p, idx_bytes=idx_bytes)
         return sa, lcp
     return oracle_lib.port_sa_lcp(text, subproblems=p, idx_bytes=idx_bytes)

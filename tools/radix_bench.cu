@@ -1,0 +1,70 @@
+// Micro-benchmark of one radix pass (not product code): times radix_hist / radix_scatter on
+// uniformly random 64-bit keys + 32-bit values.  usage: radix_bench [n] [reps] [shift]
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../caps-sa_b200/csrc/radix_sort.cuh"
+
+namespace capsb {
+std::atomic<uint64_t> g_kernel_launches{0};
+}
+using namespace capsb;
+
+__global__ void fill_random(uint64_t* keys, uint32_t* vals, uint64_t n) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t z = i * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    keys[i] = z ^ (z >> 31);
+    vals[i] = (uint32_t)i;
+  }
+}
+
+int main(int argc, char** argv) {
+  const uint64_t n = argc > 1 ? (uint64_t)atof(argv[1]) : 100000000ull;
+  const int reps = argc > 2 ? atoi(argv[2]) : 10;
+  const unsigned shift = argc > 3 ? atoi(argv[3]) : 0;
+  try {
+    DeviceInfo dev;
+    cudaDeviceProp prop;
+    CAPSB_CUDA(cudaGetDeviceProperties(&prop, 0));
+    dev.sm_count = prop.multiProcessorCount;
+    cudaStream_t st;
+    CAPSB_CUDA(cudaStreamCreate(&st));
+    RadixScratch rs;
+    rs.init(dev, st);
+    DevBuf<uint64_t> ka(n, st), kb(n, st);
+    DevBuf<uint32_t> va(n, st), vb(n, st);
+    fill_random<<<dev.sm_count * 8, 256, 0, st>>>(ka.get(), va.get(), n);
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    rs.timer.enabled = true;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0), cudaEventCreate(&e1);
+    for (int w = 0; w < 3; ++w)
+      radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
+                                     vb.get());
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    rs.timer.reset();
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < reps; ++r)
+      radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
+                                     vb.get());
+    cudaEventRecord(e1, st);
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    uint32_t launches = 0;
+    const float scatter_ms = rs.timer.drain(&launches);
+    const double bytes = 24.0 * n;
+    printf("n=%llu min_blocks=%d grid_per_sm=%u: pass %.4f ms (%.1f GB/s incl. hist), scatter %.4f ms (%.1f GB/s, %.3f of 6650)\n",
+           (unsigned long long)n, rs.min_blocks, rs.max_blocks / dev.sm_count, ms / reps,
+           (bytes + 8.0 * n) / (ms / reps) / 1e6, scatter_ms / launches, bytes / (scatter_ms / launches) / 1e6,
+           bytes / (scatter_ms / launches) / 1e6 / 6650.0);
+  } catch (const std::exception& e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
