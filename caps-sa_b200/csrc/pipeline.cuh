@@ -163,6 +163,36 @@ struct LocalRanks {
 
   bool any_active(uint64_t m) { return m > 0; }
 
+  // isa[sa[k]] = pos_base + k for every k in [0, count): the rank of a suffix that is alone in
+  // its key group is its final SA position.  A plain scatter is count random 4-byte writes into
+  // an array far larger than L2 (a 32 B read-modify-write in HBM each: 130 ms at 3.1 G
+  // suffixes).  So the (suffix, position) pairs are first split by the top byte of the suffix
+  // index — one counting pass of the radix machinery — after which consecutive writes stay
+  // inside one window of at most 2^24 entries that L2 holds and merges into full sectors.
+  void publish_positions(const IdxT* sa, uint64_t count, uint64_t pos_base) {
+    IdxT* d_isa = isa.get();
+    cudaStream_t st = eng.stream;
+    constexpr unsigned kWindowLog = sizeof(IdxT) == 8 ? 23 : 24;  // 64 MB of ranks per window
+    const unsigned bits = bit_length(n - 1);
+    if (bits <= kWindowLog) {  // the whole array sits in L2 anyway
+      launch_map(eng.dev, st, count, [=] __device__(uint64_t k) { d_isa[sa[k]] = static_cast<IdxT>(pos_base + k); });
+      return;
+    }
+    const unsigned shift = std::max(kWindowLog, bits - 8u);  // at most 256 windows (one digit)
+    DevBuf<IdxT> part_idx(count, st), part_rank(count, st);
+    radix_pass<IdxT, IdxT>(st, eng.radix, PositionSource{sa, pos_base}, count, shift, part_idx.get(), part_rank.get());
+    const IdxT* pi = part_idx.get();
+    const IdxT* pr = part_rank.get();
+    launch_map(eng.dev, st, count, [=] __device__(uint64_t j) { d_isa[__ldcs(pi + j)] = __ldcs(pr + j); });
+  }
+  struct PositionSource {
+    const IdxT* sa;
+    uint64_t pos_base;
+    __device__ __forceinline__ IdxT key(uint64_t k) const { return sa[k]; }
+    __device__ __forceinline__ IdxT val(uint64_t k) const { return static_cast<IdxT>(pos_base + k); }
+    static constexpr uint64_t bytes_read_per_item() { return sizeof(IdxT); }
+  };
+
   // isa[idx[t]] = head[t] for t in [0, m)
   void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
     IdxT* d_isa = isa.get();
@@ -200,19 +230,14 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
 
-  DevBuf<IdxT> group_of(count, st);  // local SA position -> global SA position of its group's head
-  IdxT* d_group = group_of.get();
-  scan_full<IdxT, OpMax, true>(
-      eng, count,
-      [=] __device__(uint64_t k) -> IdxT {
-        return (k == 0 || keys[k] != keys[k - 1]) ? static_cast<IdxT>(pos_base + k) : IdxT(0);
-      },
-      [=] __device__(uint64_t k, IdxT head) { d_group[k] = head; });
-  ranks.publish(d_sa, d_group, count);
+  // every suffix starts with its SA position as rank; members of a key group then share the
+  // position of the group's first member
+  ranks.publish_positions(d_sa, count, pos_base);
 
+  // the suffixes still to be ordered: members of key groups with at least two suffixes
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
-    const bool single = d_group[k] == pos_base + k && (k + 1 == count || d_group[k + 1] == pos_base + k + 1);
-    return single ? IdxT(0) : IdxT(1);
+    const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
+    return tied ? IdxT(1) : IdxT(0);
   };
   uint64_t m = scan_total<IdxT, OpSum>(eng, count, in_group);
   DevBuf<IdxT> a_pos(m, st), a_idx(m, st), a_group(m, st);
@@ -221,15 +246,22 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d
     IdxT* s = a_idx.get();
     IdxT* g = a_group.get();
     scan_finish<IdxT, OpSum, false>(eng, count, in_group, [=] __device__(uint64_t k, IdxT slot) {
-      const bool single = d_group[k] == pos_base + k && (k + 1 == count || d_group[k + 1] == pos_base + k + 1);
-      if (!single) {
+      const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
+      if (tied) {
         p[slot] = static_cast<IdxT>(k);
         s[slot] = d_sa[k];
-        g[slot] = d_group[k];
       }
     });
+    // group head (global SA position) of every active suffix: running maximum of the heads
+    scan_full<IdxT, OpMax, true>(
+        eng, m,
+        [=] __device__(uint64_t t) -> IdxT {
+          const uint64_t k = p[t];
+          return (k == 0 || keys[k] != keys[k - 1]) ? static_cast<IdxT>(pos_base + k) : IdxT(0);
+        },
+        [=] __device__(uint64_t t, IdxT head) { g[t] = head; });
   }
-  group_of.release();
+  ranks.publish(a_idx.get(), a_group.get(), m);
 
   const unsigned rank_bits = round_up8(bit_length(n - 1));
   uint64_t h = h0;

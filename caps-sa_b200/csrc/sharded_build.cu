@@ -142,16 +142,30 @@ struct ShardedRanks {
     return false;
   }
 
-  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
+  // isa[idx(t)] = rank(t) on the rank that owns text position idx(t), for t in [0, m)
+  template <class IdxFn, class RankFn>
+  void publish_with(uint64_t m, IdxFn idx, RankFn rank_of) {
     const SliceMap mp = map;
-    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(idx[t]); });
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(idx(t)); });
     DevBuf<IdxPair<IdxT>> recv(rt.recv_total, eng.stream);
     route_forward<IdxPair<IdxT>>(
-        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{idx[t], head[t]}; }, recv.get());
+        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{idx(t), rank_of(t)}; },
+        recv.get());
     IdxT* isa = isa_local.get();
     const IdxPair<IdxT>* rv = recv.get();
     const uint64_t lo_ = lo;
     launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { isa[rv[j].a - lo_] = rv[j].b; });
+  }
+
+  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
+    publish_with(
+        m, [=] __device__(uint64_t t) -> IdxT { return idx[t]; }, [=] __device__(uint64_t t) -> IdxT { return head[t]; });
+  }
+
+  void publish_positions(const IdxT* sa, uint64_t count, uint64_t pos_base) {
+    publish_with(
+        count, [=] __device__(uint64_t k) -> IdxT { return sa[k]; },
+        [=] __device__(uint64_t k) -> IdxT { return static_cast<IdxT>(pos_base + k); });
   }
 
   void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {

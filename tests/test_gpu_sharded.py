@@ -101,3 +101,21 @@ def test_sharded_bad_device_fails_loudly(pkg, synth):
     obj = pkg.SuffixArray(text, devices=[0, 99])
     with pytest.raises(pkg.CapsSaError):
         obj.construct()
+
+
+def test_one_process_per_gpu_nccl(pkg):
+    """torchrun + NCCL transport (needs at least two GPUs; skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+
+    visible = pkg.lib().caps_sa_gpu_device_count()
+    if visible < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(visible, 4)
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tools", "sharded_check.py")],
+        capture_output=True, text=True, timeout=900)
+    assert proc.returncode == 0 and "SHARDED_CHECK PASSED" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
