@@ -73,6 +73,7 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
   }
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     if (n == 0) return CAPS_SA_GPU_OK;
     cudaStream_t st = eng.stream;
@@ -102,6 +103,7 @@ int construct_device(caps_sa_gpu_engine* engine, const void* d_text, uint64_t n,
   if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     capsb::StreamScope scope(eng, stream ? static_cast<cudaStream_t>(stream) : eng.stream);
     capsb::build_sa_lcp<IdxT>(eng, static_cast<const uint8_t*>(d_text), n, d_sa, d_lcp);
     return CAPS_SA_GPU_OK;
@@ -167,6 +169,7 @@ int construct_multi(const int* devices, int num_ranks, const char* text, uint64_
       threads.emplace_back([&, r] {
         try {
           Engine eng(devices[r]);
+          capsb::ArenaScope arena_scope(&eng.arena);
           capsb::ThreadComm comm(group, r, devices[r]);
           if (n) {
             cudaStream_t st = eng.stream;
@@ -214,6 +217,7 @@ int construct_sharded_device(caps_sa_gpu_engine* engine, const void* d_text, uin
   if (!engine->impl.comm) return bad_args("the engine has not joined a communicator (caps_sa_gpu_engine_comm_init)");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     capsb::StreamScope scope(eng, stream ? static_cast<cudaStream_t>(stream) : eng.stream);
     capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, static_cast<const uint8_t*>(d_text), n, shard_of<IdxT>(eng));
     return CAPS_SA_GPU_OK;
@@ -228,6 +232,7 @@ int construct_sharded_host(caps_sa_gpu_engine* engine, const char* text, uint64_
   if (!engine->impl.comm) return bad_args("the engine has not joined a communicator (caps_sa_gpu_engine_comm_init)");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     if (n == 0) return CAPS_SA_GPU_OK;
     cudaStream_t st = eng.stream;
@@ -347,6 +352,7 @@ int caps_sa_gpu_engine_comm_init(caps_sa_gpu_engine* engine, const void* id, int
   if (world < 1 || rank < 0 || rank >= world) return bad_args("bad rank / world size");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     eng.comm.reset();
     if (world == 1)
       eng.comm.reset(new capsb::SelfComm());
@@ -375,6 +381,7 @@ int caps_sa_gpu_shard_copy(caps_sa_gpu_engine* engine, void* sa_dst, void* lcp_d
   if (!engine) return bad_args("engine is NULL");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     const cudaMemcpyKind kind = to_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
     const bool wide = eng.stats.idx_bytes == 8;
@@ -397,6 +404,7 @@ int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n) {
   if (n > 0 && !text) return bad_args("NULL buffer");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     if (n == 0) return CAPS_SA_GPU_OK;
     capsb::DevBuf<uint8_t> d(n, eng.stream);
@@ -427,6 +435,7 @@ int caps_sa_gpu_stage_pack(caps_sa_gpu_engine* engine, const char* text, uint64_
   int bits = 0;
   const int rc = guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     capsb::DevBuf<uint8_t> d(n ? n : 1, eng.stream);
     CAPSB_CUDA(cudaMemcpyAsync(d.get(), text, n, cudaMemcpyHostToDevice, eng.stream));
@@ -448,6 +457,7 @@ int caps_sa_gpu_stage_radix_sort_u64_u32(caps_sa_gpu_engine* engine, uint64_t* k
   if (end_bit > 64 || begin_bit >= end_bit) return bad_args("bad bit range");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     if (n == 0) return CAPS_SA_GPU_OK;
     cudaStream_t st = eng.stream;
@@ -468,6 +478,7 @@ int caps_sa_gpu_stage_scan_u32(caps_sa_gpu_engine* engine, uint32_t* data, uint6
   if (!engine || (n && !data)) return bad_args("NULL argument");
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
     CAPSB_CUDA(cudaSetDevice(eng.dev.device));
     if (n == 0) return CAPS_SA_GPU_OK;
     cudaStream_t st = eng.stream;

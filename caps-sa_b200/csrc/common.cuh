@@ -14,6 +14,10 @@
 
 #include <atomic>
 #include <cstdint>
+#include <iterator>
+#include <map>
+#include <unordered_map>
+#include <vector>
 #include <cstdio>
 #include <stdexcept>
 #include <string>
@@ -71,7 +75,161 @@ inline Chunking make_chunking(uint64_t n, unsigned tile, unsigned max_blocks) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Stream-ordered device buffer
+// Device memory arena
+//
+// All scratch of one engine comes from a few large cudaMalloc slabs that the engine keeps
+// between constructions, sub-allocated first-fit with coalescing on the host.  Everything an
+// engine does is ordered on one stream, so a block can be handed out again the moment it is
+// freed.  (The stream-ordered pool of the driver, cudaMallocAsync, was measured to remap
+// physical pages when multi-GB blocks of changing sizes are recycled: stages of the sharded
+// path took 1-2 s instead of 50 ms — profiles/r01/README.md.)
+// ---------------------------------------------------------------------------------------
+class Arena {
+ public:
+  Arena() = default;
+  Arena(const Arena&) = delete;
+  Arena& operator=(const Arena&) = delete;
+  ~Arena() { release_all(); }
+
+  void* alloc(size_t bytes) {
+    const size_t need = round_up(bytes ? bytes : 1, kAlign);
+    if (void* p = take(need)) return p;
+    add_slab(need);  // no hole fits
+    void* p = take(need);
+    if (!p) fail("internal: arena allocation failed after adding a slab");
+    return p;
+  }
+
+  void free(void* p) {
+    auto it = live_.find(p);
+    if (it == live_.end()) return;
+    const Live l = it->second;
+    live_.erase(it);
+    used_ -= l.size;
+    Slab& slab = slabs_[l.slab];
+    size_t off = static_cast<size_t>(static_cast<char*>(p) - slab.base), len = l.size;
+    auto next = slab.free_blocks.lower_bound(off);
+    if (next != slab.free_blocks.end() && off + len == next->first) {
+      len += next->second;
+      next = slab.free_blocks.erase(next);
+    }
+    if (next != slab.free_blocks.begin()) {
+      auto prev = std::prev(next);
+      if (prev->first + prev->second == off) {
+        off = prev->first;
+        len += prev->second;
+        slab.free_blocks.erase(prev);
+      }
+    }
+    slab.free_blocks.emplace(off, len);
+  }
+
+  // Returns every slab to the driver (all blocks must have been freed or are abandoned).
+  void release_all() {
+    for (Slab& slab : slabs_)
+      if (slab.base) cudaFree(slab.base);
+    slabs_.clear();
+    live_.clear();
+    reserved_ = used_ = 0;
+  }
+
+  size_t reserved() const { return reserved_; }
+  size_t used() const { return used_; }
+
+  // The arena DevBuf allocates from on this host thread (nullptr: the driver's stream-ordered pool).
+  static Arena*& current() {
+    static thread_local Arena* arena = nullptr;
+    return arena;
+  }
+
+ private:
+  static constexpr size_t kAlign = 512;
+  static constexpr size_t kMinSlab = 32ull << 20;
+  static constexpr size_t kSlabAlign = 2ull << 20;
+  static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+  struct Slab {
+    char* base = nullptr;
+    size_t size = 0;
+    std::map<size_t, size_t> free_blocks;  // offset -> length
+  };
+  struct Live {
+    size_t slab;
+    size_t size;
+  };
+
+  // First fit over the slabs' free blocks.
+  void* take(size_t need) {
+    for (size_t s = 0; s < slabs_.size(); ++s) {
+      Slab& slab = slabs_[s];
+      for (auto it = slab.free_blocks.begin(); it != slab.free_blocks.end(); ++it) {
+        if (it->second < need) continue;
+        const size_t off = it->first, len = it->second;
+        slab.free_blocks.erase(it);
+        if (len > need) slab.free_blocks.emplace(off + need, len - need);
+        void* p = slab.base + off;
+        live_.emplace(p, Live{s, need});
+        used_ += need;
+        return p;
+      }
+    }
+    return nullptr;
+  }
+
+  // A new slab for a request of `need` bytes (small requests share slabs of kMinSlab).
+  void add_slab(size_t need) {
+    const size_t slab_bytes = round_up(need > kMinSlab ? need : kMinSlab, kSlabAlign);
+    void* base = nullptr;
+    cudaError_t err = cudaMalloc(&base, slab_bytes);
+    if (err != cudaSuccess && drop_empty_slabs()) {  // give unused slabs back and retry once
+      cudaGetLastError();
+      err = cudaMalloc(&base, slab_bytes);
+    }
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      fail("out of device memory: cudaMalloc(" + std::to_string(slab_bytes) + " bytes) failed: " +
+           cudaGetErrorString(err) + " (arena holds " + std::to_string(reserved_) + " bytes, " +
+           std::to_string(used_) + " in use)");
+    }
+    Slab slab;
+    slab.base = static_cast<char*>(base);
+    slab.size = slab_bytes;
+    slab.free_blocks.emplace(0, slab_bytes);
+    slabs_.push_back(std::move(slab));
+    reserved_ += slab_bytes;
+  }
+
+  // Frees slabs that hold no live block (the vector keeps their slots: indices stay valid).
+  bool drop_empty_slabs() {
+    bool any = false;
+    for (Slab& slab : slabs_) {
+      if (slab.base && slab.free_blocks.size() == 1 && slab.free_blocks.begin()->second == slab.size) {
+        cudaFree(slab.base);
+        reserved_ -= slab.size;
+        slab.base = nullptr;
+        slab.size = 0;
+        slab.free_blocks.clear();
+        any = true;
+      }
+    }
+    return any;
+  }
+
+  std::vector<Slab> slabs_;
+  std::unordered_map<void*, Live> live_;
+  size_t reserved_ = 0, used_ = 0;
+};
+
+struct ArenaScope {
+  Arena* saved;
+  explicit ArenaScope(Arena* a) : saved(Arena::current()) { Arena::current() = a; }
+  ~ArenaScope() { Arena::current() = saved; }
+  ArenaScope(const ArenaScope&) = delete;
+  ArenaScope& operator=(const ArenaScope&) = delete;
+};
+
+// ---------------------------------------------------------------------------------------
+// Device buffer: from the calling thread's arena if one is active, else stream-ordered
 // ---------------------------------------------------------------------------------------
 template <class T>
 class DevBuf {
@@ -84,8 +242,8 @@ class DevBuf {
   DevBuf& operator=(DevBuf&& o) noexcept {
     if (this != &o) {
       release();
-      ptr_ = o.ptr_, count_ = o.count_, stream_ = o.stream_;
-      o.ptr_ = nullptr, o.count_ = 0;
+      ptr_ = o.ptr_, count_ = o.count_, stream_ = o.stream_, arena_ = o.arena_;
+      o.ptr_ = nullptr, o.count_ = 0, o.arena_ = nullptr;
     }
     return *this;
   }
@@ -96,6 +254,11 @@ class DevBuf {
     stream_ = stream;
     count_ = count;
     if (count == 0) return;
+    arena_ = Arena::current();
+    if (arena_) {
+      ptr_ = static_cast<T*>(arena_->alloc(count * sizeof(T)));
+      return;
+    }
     void* p = nullptr;
     cudaError_t err = cudaMallocAsync(&p, count * sizeof(T), stream);
     if (err != cudaSuccess) {
@@ -106,9 +269,15 @@ class DevBuf {
     ptr_ = static_cast<T*>(p);
   }
   void release() {
-    if (ptr_) cudaFreeAsync(ptr_, stream_);
+    if (ptr_) {
+      if (arena_)
+        arena_->free(ptr_);
+      else
+        cudaFreeAsync(ptr_, stream_);
+    }
     ptr_ = nullptr;
     count_ = 0;
+    arena_ = nullptr;
   }
   T* get() const { return ptr_; }
   uint64_t size() const { return count_; }
@@ -118,6 +287,7 @@ class DevBuf {
   T* ptr_ = nullptr;
   uint64_t count_ = 0;
   cudaStream_t stream_ = nullptr;
+  Arena* arena_ = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------
@@ -242,22 +412,36 @@ __global__ void __launch_bounds__(kScanThreads) scan_spine_kernel(unsigned count
   if (threadIdx.x == 0 && total_out) *total_out = carry;
 }
 
+// Shared-memory slot of tile element e: one pad word per 8 elements makes both access patterns
+// conflict-free — striped (e = k*256 + t, the coalesced global order) and blocked (e = 8t + k,
+// the order the scan needs).
+__device__ __forceinline__ unsigned scan_slot(unsigned e) { return e + (e >> 3); }
+
+// `in` and `out` are called in striped order (consecutive threads = consecutive elements) so the
+// loads/stores inside the functors coalesce; the values cross to the blocked arrangement of the
+// scan through shared memory.
 template <class T, class Op, bool Inclusive, class In, class Out>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t n, uint64_t chunk, In in,
                                                                   Out out, const T* partial) {
   __shared__ T smem[kScanThreads / 32];
+  __shared__ T stage[kScanTile + kScanTile / 8];
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
   T carry = partial[blockIdx.x];
   for (uint64_t tile = begin; tile < end; tile += kScanTile) {
-    // blocked arrangement: thread t owns items [t*kScanItems, (t+1)*kScanItems)
-    const uint64_t first = tile + static_cast<uint64_t>(threadIdx.x) * kScanItems;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const unsigned e = static_cast<unsigned>(k) * kScanThreads + threadIdx.x;
+      const uint64_t i = tile + e;
+      stage[scan_slot(e)] = i < end ? in(i) : Op::template identity<T>();
+    }
+    __syncthreads();
+    // blocked arrangement: thread t owns elements [t*kScanItems, (t+1)*kScanItems)
     T vals[kScanItems];
     T local = Op::template identity<T>();
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-      const uint64_t i = first + k;
-      vals[k] = i < end ? in(i) : Op::template identity<T>();
+      vals[k] = stage[scan_slot(threadIdx.x * kScanItems + k)];
       local = Op::template apply<T>(local, vals[k]);
     }
     T inc, total;
@@ -265,12 +449,19 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t n, ui
     T run = Op::template apply<T>(carry, excl);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-      const uint64_t i = first + k;
       const T next = Op::template apply<T>(run, vals[k]);
-      if (i < end) out(i, Inclusive ? next : run);
+      stage[scan_slot(threadIdx.x * kScanItems + k)] = Inclusive ? next : run;
       run = next;
     }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const unsigned e = static_cast<unsigned>(k) * kScanThreads + threadIdx.x;
+      const uint64_t i = tile + e;
+      if (i < end) out(i, stage[scan_slot(e)]);
+    }
     carry = Op::template apply<T>(carry, total);
+    __syncthreads();  // the staging area is rewritten by the next tile
   }
 }
 

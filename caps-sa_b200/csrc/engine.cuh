@@ -54,6 +54,7 @@ struct ShardResult {
 };
 
 struct Engine {
+  Arena arena;  // first member: outlives every buffer below
   DeviceInfo dev;
   cudaStream_t stream = nullptr;      // stream all work is issued on
   cudaStream_t own_stream = nullptr;  // created with the engine

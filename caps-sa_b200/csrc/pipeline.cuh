@@ -67,12 +67,30 @@ struct TextSource {
   static constexpr uint64_t bytes_read_per_item() { return 1; }
 };
 
+// CAPSB_TRACE=1: per-stage / per-round log on stderr (host clock, pool occupancy)
+inline bool trace_enabled() {
+  static const bool on = std::getenv("CAPSB_TRACE") != nullptr;
+  return on;
+}
+inline void trace_point(Engine& eng, const char* what) {
+  if (!trace_enabled()) return;
+  static const auto t0 = std::chrono::steady_clock::now();
+  cudaStreamSynchronize(eng.stream);
+  const uint64_t reserved = eng.arena.reserved(), used = eng.arena.used();
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  std::fprintf(stderr, "[capsb dev%d] %10.3f ms  %-22s arena reserved %.2f GB used %.2f GB, device free %.2f GB\n",
+               eng.dev.device, ms, what, reserved / 1e9, used / 1e9, free_b / 1e9);
+}
+
 // Stage timer: records an event now; elapsed times are read at the end.
 struct StageClock {
   Engine& eng;
   std::vector<cudaEvent_t> marks;
   explicit StageClock(Engine& e) : eng(e) {}
-  void mark() {
+  void mark(const char* what = "stage") {
+    trace_point(eng, what);
     cudaEvent_t ev;
     if (!eng.events.empty()) {
       ev = eng.events.back();
@@ -150,48 +168,34 @@ void sort_suffix_slice(Engine& eng, const PackedText& pt, uint64_t base, uint64_
 }
 
 // ---------------------------------------------------------------------------------------
-// Rank storage of the single-GPU path: one array isa[text position] = first SA position of the
-// suffix's current group.
+// Rank storage of the single-GPU path: isa[text position] = first SA position of the
+// suffix's current group — but only for suffixes that were ever tied.  A suffix whose key is
+// unique never enters the refinement; its rank is its final SA position, which is the position
+// of its key in the sorted key array.  Writing those n ranks up front is a random scatter into
+// an array far larger than L2 (a 32 B read-modify-write in HBM per 4-byte rank: 130 ms at
+// 3.1 G suffixes, and partitioning the scatter into L2-sized windows first was no faster —
+// profiles/r01/README.md), so the array is filled with a sentinel instead (one streaming
+// memset) and a lookup that hits the sentinel binary-searches the suffix's key.
 // ---------------------------------------------------------------------------------------
 template <class IdxT>
 struct LocalRanks {
   using Comp = typename IdxTraits<IdxT>::Comp;
+  static constexpr IdxT kUnset = ~IdxT(0);  // never a group head: heads of tied groups are <= n - 2
   Engine& eng;
   uint64_t n;
+  PackedText pt;
+  const uint64_t* keys;  // sorted (masked) keys of all n suffixes
+  uint64_t key_mask;
   DevBuf<IdxT> isa;
-  LocalRanks(Engine& e, uint64_t n_) : eng(e), n(n_), isa(n_, e.stream) {}
+  LocalRanks(Engine& e, uint64_t n_, const PackedText& pt_, const uint64_t* keys_, uint64_t key_mask_)
+      : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_), isa(n_, e.stream) {}
 
   bool any_active(uint64_t m) { return m > 0; }
 
-  // isa[sa[k]] = pos_base + k for every k in [0, count): the rank of a suffix that is alone in
-  // its key group is its final SA position.  A plain scatter is count random 4-byte writes into
-  // an array far larger than L2 (a 32 B read-modify-write in HBM each: 130 ms at 3.1 G
-  // suffixes).  So the (suffix, position) pairs are first split by the top byte of the suffix
-  // index — one counting pass of the radix machinery — after which consecutive writes stay
-  // inside one window of at most 2^24 entries that L2 holds and merges into full sectors.
-  void publish_positions(const IdxT* sa, uint64_t count, uint64_t pos_base) {
-    IdxT* d_isa = isa.get();
-    cudaStream_t st = eng.stream;
-    constexpr unsigned kWindowLog = sizeof(IdxT) == 8 ? 23 : 24;  // 64 MB of ranks per window
-    const unsigned bits = bit_length(n - 1);
-    if (bits <= kWindowLog) {  // the whole array sits in L2 anyway
-      launch_map(eng.dev, st, count, [=] __device__(uint64_t k) { d_isa[sa[k]] = static_cast<IdxT>(pos_base + k); });
-      return;
-    }
-    const unsigned shift = std::max(kWindowLog, bits - 8u);  // at most 256 windows (one digit)
-    DevBuf<IdxT> part_idx(count, st), part_rank(count, st);
-    radix_pass<IdxT, IdxT>(st, eng.radix, PositionSource{sa, pos_base}, count, shift, part_idx.get(), part_rank.get());
-    const IdxT* pi = part_idx.get();
-    const IdxT* pr = part_rank.get();
-    launch_map(eng.dev, st, count, [=] __device__(uint64_t j) { d_isa[__ldcs(pi + j)] = __ldcs(pr + j); });
+  // every suffix starts with its SA position as rank: implicit (see above)
+  void publish_positions(const IdxT*, uint64_t, uint64_t) {
+    CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream));
   }
-  struct PositionSource {
-    const IdxT* sa;
-    uint64_t pos_base;
-    __device__ __forceinline__ IdxT key(uint64_t k) const { return sa[k]; }
-    __device__ __forceinline__ IdxT val(uint64_t k) const { return static_cast<IdxT>(pos_base + k); }
-    static constexpr uint64_t bytes_read_per_item() { return sizeof(IdxT); }
-  };
 
   // isa[idx[t]] = head[t] for t in [0, m)
   void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
@@ -205,11 +209,31 @@ struct LocalRanks {
     constexpr unsigned kField = IdxTraits<IdxT>::kField;
     const IdxT* d_isa = isa.get();
     const uint64_t n_ = n;
+    const PackedText text = pt;
+    const uint64_t* sorted_keys = keys;
+    const uint64_t mask = key_mask;
     launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) {
       const uint64_t i = idx[t];
       const uint64_t ih = i + h;
       const bool inside = ih < n_;
-      const uint64_t second = inside ? static_cast<uint64_t>(d_isa[ih]) : (n_ - 1 - i);
+      uint64_t second = n_ - 1 - i;
+      if (inside) {
+        const IdxT r = d_isa[ih];
+        if (r != kUnset) {
+          second = r;
+        } else {  // never tied: the position of its (unique) key among the sorted keys
+          const uint64_t want = text.window(ih) & mask;
+          uint64_t lo = 0, hi = n_;
+          while (lo < hi) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (sorted_keys[mid] < want)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          second = lo;
+        }
+      }
       comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
                 static_cast<Comp>(second);
     });
@@ -265,7 +289,7 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d
 
   const unsigned rank_bits = round_up8(bit_length(n - 1));
   uint64_t h = h0;
-  static const bool trace = std::getenv("CAPSB_TRACE") != nullptr;  // per-round log on stderr
+  const bool trace = trace_enabled();
   std::chrono::steady_clock::time_point round_start;
   if (trace) {
     CAPSB_CUDA(cudaStreamSynchronize(st));

@@ -25,13 +25,9 @@ Engine::Engine(int device) {
   cudaDeviceProp prop;
   CAPSB_CUDA(cudaGetDeviceProperties(&prop, device));
   dev.sm_count = prop.multiProcessorCount;
+  ArenaScope scope(&arena);
   CAPSB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
   stream = own_stream;
-  // keep freed scratch cached in the pool between constructions
-  cudaMemPool_t pool;
-  CAPSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t threshold = ~0ull;
-  CAPSB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   radix.init(dev, stream);
   scan32.init(dev, stream);
   scan64.init(dev, stream);
@@ -94,7 +90,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   } else {
     // ---- 4. prefix-doubling refinement of the tied groups --------------------------------
     {
-      LocalRanks<IdxT> ranks(eng, n);
+      LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
       refine_tied_groups<IdxT>(eng, ranks, keys, d_sa, n, 0, n, key_bits >> log2_bits);
     }
     key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);

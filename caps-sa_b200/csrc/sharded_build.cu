@@ -259,7 +259,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) fail("text too long for 32-bit indices");
 
   StageClock clock(eng);
-  clock.mark();  // 0
+  clock.mark("begin");  // 0
 
   // ---- text staging + key packing (whole text, every rank) -------------------------------
   PackedTextBuf packed = pack_text(eng, d_text, n);
@@ -267,7 +267,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   const unsigned log2_bits = pt.log2_bits;
   eng.stats.bits_per_symbol = pt.bits();
   eng.stats.alphabet_size = packed.sigma;
-  clock.mark();  // 1
+  clock.mark("packed");  // 1
 
   // ---- slice sort ------------------------------------------------------------------------
   const SliceMap map{n, n / world, world};
@@ -278,7 +278,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   DevBuf<uint64_t> slice_keys(slice_count, st);
   DevBuf<IdxT> slice_idx(slice_count, st);
   sort_suffix_slice<IdxT>(eng, pt, lo, slice_count, key_bits, slice_keys.get(), slice_idx.get());
-  clock.mark();  // 2
+  clock.mark("slice sorted");  // 2
 
   // ---- pivots: regular samples, all-gather, every rank sorts the same sample set ----------
   const uint64_t sample_total = static_cast<uint64_t>(kSamplesPerRank) * world;
@@ -332,7 +332,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   comm.all_to_all_v(slice_idx.get(), send_counts.data(), out.sa.get(), recv_counts.data(), sizeof(IdxT), st);
   slice_keys.release();
   slice_idx.release();
-  clock.mark();  // 3
+  clock.mark("exchanged");  // 3
 
   // ---- bucket merge ------------------------------------------------------------------------
   {
@@ -349,7 +349,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   bucket_idx_tmp.release();
   const uint64_t* keys = bucket_keys.get();
   IdxT* d_sa = out.sa.get();
-  clock.mark();  // 4
+  clock.mark("merged");  // 4
 
   // ---- ties ---------------------------------------------------------------------------------
   auto tied = [=] __device__(uint64_t k) -> uint64_t { return (k > 0 && keys[k] == keys[k - 1]) ? 1u : 0u; };
@@ -365,7 +365,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     ShardedRanks<IdxT> ranks(eng, comm, map);
     refine_tied_groups<IdxT>(eng, ranks, keys, d_sa, bucket_count, bucket_offset, n, key_bits >> log2_bits);
   }
-  clock.mark();  // 5
+  clock.mark("ties resolved");  // 5
 
   // ---- LCP ----------------------------------------------------------------------------------
   out.lcp.alloc(bucket_count, st);
@@ -443,7 +443,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     route_backward<IdxT>(eng, comm, rt, answers.get(),
                          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[pk[t]] = lcp; });
   }
-  clock.mark();  // 6
+  clock.mark("lcp done");  // 6
   CAPSB_CUDA(cudaStreamSynchronize(st));
 
   eng.stats.ms_pack = clock.between(0, 1);
