@@ -35,6 +35,11 @@ struct IdxTraits<uint64_t> {
   static constexpr unsigned kField = 64;
 };
 
+template <class IdxT>
+struct IdxPair {
+  IdxT a, b;
+};
+
 inline unsigned bit_length(uint64_t v) {
   unsigned b = 0;
   while (v) ++b, v >>= 1;
@@ -193,9 +198,7 @@ struct LocalRanks {
   bool any_active(uint64_t m) { return m > 0; }
 
   // every suffix starts with its SA position as rank: implicit (see above)
-  void publish_positions(const IdxT*, uint64_t, uint64_t) {
-    CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream));
-  }
+  void reset() { CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream)); }
 
   // isa[idx[t]] = head[t] for t in [0, m)
   void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
@@ -246,29 +249,199 @@ struct LocalRanks {
 // order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
 // keys must be complete inside [0, count).
 // ---------------------------------------------------------------------------------------
-template <class IdxT, class Ranks>
-void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d_sa, uint64_t count,
-                        uint64_t pos_base, uint64_t n, uint64_t h0) {
-  using Comp = typename IdxTraits<IdxT>::Comp;
-  constexpr unsigned kField = IdxTraits<IdxT>::kField;
+constexpr unsigned kSmallGroup = 32;  // groups up to this size are ordered by counting, not sorting
+
+// The suffixes still being ordered, in SA order; the members of a group are consecutive.
+template <class IdxT>
+struct ActiveList {
+  uint64_t m = 0;
+  DevBuf<IdxT> pos;    // local SA position
+  DevBuf<IdxT> idx;    // suffix (text position)
+  DevBuf<IdxT> group;  // global SA position of the group's first member
+};
+
+// One refinement round on the active list.  comp_a[t] = group field (the group head plus one
+// for suffixes that reach depth h inside the text) above a `second` field whose bits
+// [second_lo, second_hi) order the members of a group; CompT's group field starts at bit
+// kGroupShift.  Orders every group, writes the new order to d_sa, publishes the new group heads
+// and drops the suffixes that are now alone in their group.
+template <class IdxT, class CompT, unsigned kGroupShift, class Ranks>
+void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_base, DevBuf<CompT> comp_a,
+                  unsigned second_lo, unsigned second_hi, unsigned rank_bits, Ranks& ranks) {
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
+  const uint64_t m = act.m;
+  DevBuf<CompT> comp_b(m, st);
+  DevBuf<IdxT> idx_b(m, st), head_slot(m, st);
 
-  // every suffix starts with its SA position as rank; members of a key group then share the
-  // position of the group's first member
-  ranks.publish_positions(d_sa, count, pos_base);
+  // Order every group by the second field.  Groups of at most kSmallGroup suffixes — after the
+  // first rounds nearly all of them: pairs left by long exact repeats — are ranked by counting
+  // inside the group (one pass, no sort); the rest is radix-sorted by (group, second).
+  CompT* sorted_c = comp_b.get();
+  IdxT* sorted_i = idx_b.get();
+  DevBuf<uint8_t> big_flag(m, st);
+  {
+    const CompT* c = comp_a.get();
+    const IdxT* s = act.idx.get();
+    const IdxT* g = act.group.get();
+    const IdxT* p = act.pos.get();
+    uint8_t* big = big_flag.get();
+    launch_map(dev, st, m, [=] __device__(uint64_t t) {
+      const IdxT grp = g[t];
+      // the members of a group are consecutive in the list, in SA order
+      const uint64_t first = t - (static_cast<uint64_t>(p[t]) - (static_cast<uint64_t>(grp) - pos_base));
+      if (first + kSmallGroup < m && g[first + kSmallGroup] == grp) {
+        big[t] = 1;
+        return;
+      }
+      big[t] = 0;
+      const CompT mine = c[t];
+      unsigned rank = 0;
+      for (uint64_t u = first; u < m && u < first + kSmallGroup && g[u] == grp; ++u) {
+        const CompT other = c[u];
+        rank += (other < mine || (other == mine && u < t)) ? 1u : 0u;
+      }
+      sorted_c[first + rank] = mine;
+      sorted_i[first + rank] = s[t];
+    });
+  }
+  {
+    const uint8_t* big = big_flag.get();
+    auto is_big = [=] __device__(uint64_t t) -> IdxT { return big[t]; };
+    const uint64_t big_count = scan_total<IdxT, OpSum>(eng, m, is_big);
+    eng.stats.refine_sorted += big_count;
+    eng.stats.refine_counted += m - big_count;
+    if (trace_enabled())
+      std::fprintf(stderr, "[capsb]   round: %llu suffixes in small groups (counted), %llu in large groups (sorted)\n",
+                   (unsigned long long)(m - big_count), (unsigned long long)big_count);
+    if (big_count > 0) {
+      DevBuf<CompT> bc_a(big_count, st), bc_b(big_count, st);
+      DevBuf<IdxT> bi_a(big_count, st), bi_b(big_count, st), slot_of(big_count, st);
+      {
+        const CompT* c = comp_a.get();
+        const IdxT* s = act.idx.get();
+        CompT* bc = bc_a.get();
+        IdxT* bi = bi_a.get();
+        IdxT* so = slot_of.get();
+        scan_finish<IdxT, OpSum, false>(eng, m, is_big, [=] __device__(uint64_t t, IdxT j) {
+          if (big[t]) {
+            bc[j] = c[t];
+            bi[j] = s[t];
+            so[j] = static_cast<IdxT>(t);
+          }
+        });
+      }
+      // LSD over the second field, then the group field
+      CompT* kin = bc_a.get();
+      IdxT* vin = bi_a.get();
+      CompT* kout = bc_b.get();
+      IdxT* vout = bi_b.get();
+      auto passes = [&](unsigned lo, unsigned hi) {
+        for (unsigned shift = lo; shift < hi; shift += 8) {
+          radix_pass<CompT, IdxT>(st, eng.radix, ArraySource<CompT, IdxT>{kin, vin}, big_count, shift, kout, vout);
+          std::swap(kin, kout);
+          std::swap(vin, vout);
+        }
+      };
+      passes(second_lo, second_hi);
+      passes(kGroupShift, kGroupShift + rank_bits);
+      // the sorted sub-list keeps the groups in list order, so its j-th element belongs in the
+      // j-th slot that a large group occupies
+      const IdxT* so = slot_of.get();
+      const CompT* sc = kin;
+      const IdxT* si = vin;
+      launch_map(dev, st, big_count, [=] __device__(uint64_t j) {
+        sorted_c[so[j]] = sc[j];
+        sorted_i[so[j]] = si[j];
+      });
+    }
+  }
+  const CompT* sorted_comp = sorted_c;
+  const IdxT* sorted_idx = sorted_i;
+
+  IdxT* hs = head_slot.get();
+  scan_full<IdxT, OpMax, true>(
+      eng, m,
+      [=] __device__(uint64_t t) -> IdxT {
+        return (t > 0 && sorted_comp[t] != sorted_comp[t - 1]) ? static_cast<IdxT>(t) : IdxT(0);
+      },
+      [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
+
+  DevBuf<IdxT> new_group(m, st);
+  {
+    const IdxT* p = act.pos.get();
+    IdxT* ng = new_group.get();
+    launch_map(dev, st, m, [=] __device__(uint64_t t) {
+      d_sa[p[t]] = sorted_idx[t];
+      ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
+    });
+  }
+  ranks.publish(sorted_idx, new_group.get(), m);
+
+  auto still_tied = [=] __device__(uint64_t t) -> IdxT {
+    const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
+    return single ? IdxT(0) : IdxT(1);
+  };
+  const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
+  DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
+  if (m_next > 0) {
+    const IdxT* p = act.pos.get();
+    const IdxT* ng = new_group.get();
+    IdxT* np = n_pos.get();
+    IdxT* ns = n_idx.get();
+    IdxT* ngp = n_group.get();
+    scan_finish<IdxT, OpSum, false>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
+      const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
+      if (!single) {
+        np[slot] = p[t];
+        ns[slot] = sorted_idx[t];
+        ngp[slot] = ng[t];
+      }
+    });
+  }
+  act.pos = std::move(n_pos);
+  act.idx = std::move(n_idx);
+  act.group = std::move(n_group);
+  act.m = m_next;
+}
+
+// ---------------------------------------------------------------------------------------
+// Prefix-doubling refinement.  d_sa[0..count) holds suffixes in key order (SA positions
+// pos_base .. pos_base + count of the final array); keys[] are their (masked) keys, which
+// order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
+// keys must be complete inside [0, count).
+//
+// Round 1 needs no rank array at all: the rank of suffix i + h0 after the key sort is a
+// monotone function of its key (equal exactly when the keys are equal), so the members of a
+// group are ordered by the key of their suffix i + h0, read straight from the packed text —
+// no lookups, and in the sharded path no exchange.  From round 2 on the second field is the
+// rank of suffix i + h, kept by the Ranks policy; it only ever stores ranks of suffixes that
+// have been tied (everything else is implicit, see LocalRanks / ShardedRanks).
+// ---------------------------------------------------------------------------------------
+template <class IdxT, class Ranks>
+void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
+                        IdxT* d_sa, uint64_t count, uint64_t pos_base, uint64_t n) {
+  using Comp = typename IdxTraits<IdxT>::Comp;
+  constexpr unsigned kField = IdxTraits<IdxT>::kField;
+  using Wide = unsigned __int128;
+  cudaStream_t st = eng.stream;
+
+  ranks.reset();
 
   // the suffixes still to be ordered: members of key groups with at least two suffixes
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
     const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
     return tied ? IdxT(1) : IdxT(0);
   };
-  uint64_t m = scan_total<IdxT, OpSum>(eng, count, in_group);
-  DevBuf<IdxT> a_pos(m, st), a_idx(m, st), a_group(m, st);
+  ActiveList<IdxT> act;
+  act.m = scan_total<IdxT, OpSum>(eng, count, in_group);
+  act.pos.alloc(act.m, st);
+  act.idx.alloc(act.m, st);
+  act.group.alloc(act.m, st);
   {
-    IdxT* p = a_pos.get();
-    IdxT* s = a_idx.get();
-    IdxT* g = a_group.get();
+    IdxT* p = act.pos.get();
+    IdxT* s = act.idx.get();
+    IdxT* g = act.group.get();
     scan_finish<IdxT, OpSum, false>(eng, count, in_group, [=] __device__(uint64_t k, IdxT slot) {
       const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
       if (tied) {
@@ -278,95 +451,61 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const uint64_t* keys, IdxT* d
     });
     // group head (global SA position) of every active suffix: running maximum of the heads
     scan_full<IdxT, OpMax, true>(
-        eng, m,
+        eng, act.m,
         [=] __device__(uint64_t t) -> IdxT {
           const uint64_t k = p[t];
           return (k == 0 || keys[k] != keys[k - 1]) ? static_cast<IdxT>(pos_base + k) : IdxT(0);
         },
         [=] __device__(uint64_t t, IdxT head) { g[t] = head; });
   }
-  ranks.publish(a_idx.get(), a_group.get(), m);
 
   const unsigned rank_bits = round_up8(bit_length(n - 1));
-  uint64_t h = h0;
+  const unsigned log2_bits = pt.log2_bits;
+  uint64_t h = key_bits >> log2_bits;  // the key sort ordered the suffixes by that many symbols
   const bool trace = trace_enabled();
   std::chrono::steady_clock::time_point round_start;
   if (trace) {
     CAPSB_CUDA(cudaStreamSynchronize(st));
     std::fprintf(stderr, "[capsb] refine: count=%llu active=%llu h0=%llu\n", (unsigned long long)count,
-                 (unsigned long long)m, (unsigned long long)h0);
+                 (unsigned long long)act.m, (unsigned long long)h);
   }
-  while (ranks.any_active(m)) {
+  bool first_round = true;
+  while (ranks.any_active(act.m)) {
     eng.stats.refine_rounds++;
     if (trace) round_start = std::chrono::steady_clock::now();
-    DevBuf<Comp> comp_a(m, st), comp_b(m, st);
-    DevBuf<IdxT> idx_b(m, st), head_slot(m, st);
-    ranks.make_comp(a_idx.get(), a_group.get(), m, h, comp_a.get());
-
-    // sort by (group, second rank): LSD over the second-rank field, then the group field
-    Comp* kin = comp_a.get();
-    IdxT* vin = a_idx.get();
-    Comp* kout = comp_b.get();
-    IdxT* vout = idx_b.get();
-    for (unsigned field = 0; field < 2; ++field)
-      for (unsigned shift = field * kField; shift < field * kField + rank_bits; shift += 8) {
-        radix_pass<Comp, IdxT>(st, eng.radix, ArraySource<Comp, IdxT>{kin, vin}, m, shift, kout, vout);
-        std::swap(kin, kout);
-        std::swap(vin, vout);
-      }
-    const Comp* sorted_comp = kin;
-    const IdxT* sorted_idx = vin;
-
-    IdxT* hs = head_slot.get();
-    scan_full<IdxT, OpMax, true>(
-        eng, m,
-        [=] __device__(uint64_t t) -> IdxT {
-          return (t > 0 && sorted_comp[t] != sorted_comp[t - 1]) ? static_cast<IdxT>(t) : IdxT(0);
-        },
-        [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
-
-    DevBuf<IdxT> new_group(m, st);
-    {
-      const IdxT* p = a_pos.get();
-      IdxT* ng = new_group.get();
-      launch_map(dev, st, m, [=] __device__(uint64_t t) {
-        d_sa[p[t]] = sorted_idx[t];
-        ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
+    const uint64_t m = act.m;
+    if (first_round) {
+      // second field = key of suffix i + h (top key_bits of the low 64 bits); beyond the end of
+      // the text: n - 1 - i in the same bits, under a group field one lower (shorter suffix first)
+      const IdxT* idx = act.idx.get();
+      const IdxT* group = act.group.get();
+      const PackedText text = pt;
+      const uint64_t mask = key_mask_of(key_bits);
+      const unsigned low = 64 - key_bits;
+      const uint64_t depth = h;
+      DevBuf<Wide> comp(m, st);
+      Wide* c = comp.get();
+      launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
+        const uint64_t i = idx[t];
+        const uint64_t ih = i + depth;
+        const bool inside = ih < n;
+        const uint64_t second = inside ? (text.window(ih) & mask) : ((n - 1 - i) << low);
+        c[t] = (static_cast<Wide>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << 64) |
+               static_cast<Wide>(second);
       });
+      refine_round<IdxT, Wide, 64>(eng, act, d_sa, pos_base, std::move(comp), low, 64, rank_bits, ranks);
+      first_round = false;
+    } else {
+      DevBuf<Comp> comp(m, st);
+      ranks.make_comp(act.idx.get(), act.group.get(), m, h, comp.get());
+      refine_round<IdxT, Comp, kField>(eng, act, d_sa, pos_base, std::move(comp), 0, rank_bits, rank_bits, ranks);
     }
-    ranks.publish(sorted_idx, new_group.get(), m);
-
-    auto still_tied = [=] __device__(uint64_t t) -> IdxT {
-      const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
-      return single ? IdxT(0) : IdxT(1);
-    };
-    const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
-    DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
-    if (m_next > 0) {
-      const IdxT* p = a_pos.get();
-      const IdxT* ng = new_group.get();
-      IdxT* np = n_pos.get();
-      IdxT* ns = n_idx.get();
-      IdxT* ngp = n_group.get();
-      scan_finish<IdxT, OpSum, false>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
-        const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
-        if (!single) {
-          np[slot] = p[t];
-          ns[slot] = sorted_idx[t];
-          ngp[slot] = ng[t];
-        }
-      });
-    }
-    a_pos = std::move(n_pos);
-    a_idx = std::move(n_idx);
-    a_group = std::move(n_group);
     if (trace) {
       CAPSB_CUDA(cudaStreamSynchronize(st));
       const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
       std::fprintf(stderr, "[capsb] refine round %u: h=%llu active=%llu -> %llu  %.3f ms\n", eng.stats.refine_rounds,
-                   (unsigned long long)h, (unsigned long long)m, (unsigned long long)m_next, ms);
+                   (unsigned long long)h, (unsigned long long)m, (unsigned long long)act.m, ms);
     }
-    m = m_next;
     if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
     h <<= 1;
   }
@@ -404,7 +543,7 @@ void key_lcp(Engine& eng, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp, u
 
 // Block-wide comparison for the few very long common prefixes (one CTA per pair).
 template <class IdxT, class PosJ>
-__global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const uint64_t* __restrict__ pos_i, PosJ pos_j,
+__global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const IdxT* __restrict__ pos_i, PosJ pos_j,
                                                        const IdxT* __restrict__ todo, uint64_t todo_count,
                                                        IdxT* __restrict__ plcp) {
   __shared__ unsigned long long best;
@@ -452,7 +591,7 @@ __global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const uint
 // directly: 16 packed words per thread, then one CTA per pair for the rare long ones.
 // out(t, lcp) is called once per pair.
 template <class IdxT, class PosJ, class Out>
-void plcp_for_pairs(Engine& eng, const PackedText& pt, const uint64_t* pos_i, PosJ pos_j, uint64_t m, Out out) {
+void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ pos_j, uint64_t m, Out out) {
   if (m == 0) return;
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
@@ -470,7 +609,7 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const uint64_t* pos_i, Po
       // reducible: the pair (i-1, j-1) precedes it in the list (then it IS the list's previous
       // pair) and the preceding symbols agree
       const bool chained =
-          t > 0 && pos_i[t - 1] + 1 == i && i > 0 && j > 0 && pt.symbol(i - 1) == pt.symbol(j - 1);
+          t > 0 && static_cast<uint64_t>(pos_i[t - 1]) + 1 == i && i > 0 && j > 0 && pt.symbol(i - 1) == pt.symbol(j - 1);
       ch[t] = chained ? IdxT(0) : static_cast<IdxT>(t);
       if (!chained) {
         uint64_t l = 0;
@@ -498,7 +637,7 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const uint64_t* pos_i, Po
     scan_full<IdxT, OpMax, true>(
         eng, m, [=] __device__(uint64_t t) -> IdxT { return ch[t]; },
         [=] __device__(uint64_t t, IdxT head) {
-          const uint64_t back = pos_i[t] - pos_i[head];
+          const uint64_t back = static_cast<uint64_t>(pos_i[t]) - static_cast<uint64_t>(pos_i[head]);
           out(t, static_cast<IdxT>(static_cast<uint64_t>(pl[head]) - back));
         });
   }

@@ -186,7 +186,7 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT>& sm, const 
 #pragma unroll
   for (int t = 0; t < kRsItems; ++t) {
     const unsigned off = warp_first + t * 32;
-    val[t] = (kFull || off < valid) ? src.val(tile + off) : ValT(0);
+    val[t] = (kFull || off < valid) ? src.val(tile + off) : ValT{};
   }
   __syncthreads();
 

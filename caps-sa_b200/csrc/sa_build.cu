@@ -91,34 +91,35 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     // ---- 4. prefix-doubling refinement of the tied groups --------------------------------
     {
       LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
-      refine_tied_groups<IdxT>(eng, ranks, keys, d_sa, n, 0, n, key_bits >> log2_bits);
+      refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, n, 0, n);
     }
     key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
     clock.mark();  // 4
 
     // ---- 5. LCP of the tied neighbours: permuted-LCP recurrence on the deep positions ----
     {
+      // the tied pairs (i = SA[k], j = SA[k-1]) keyed by i; j and k travel as the sort's value
       const uint64_t m = ties;
-      DevBuf<uint64_t> pos_a(m, st), pos_b(m, st);  // text position i of the later suffix
-      DevBuf<IdxT> rank_a(m, st), rank_b(m, st);     // its SA position k
+      DevBuf<IdxT> pos_a(m, st), pos_b(m, st);
+      DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
       {
-        uint64_t* pa = pos_a.get();
-        IdxT* ra = rank_a.get();
+        IdxT* pa = pos_a.get();
+        IdxPair<IdxT>* ta = tag_a.get();
         scan_full<uint64_t, OpSum, false>(eng, n, tied, [=] __device__(uint64_t k, uint64_t slot) {
           if (k > 0 && keys[k] == keys[k - 1]) {
             pa[slot] = d_sa[k];
-            ra[slot] = static_cast<IdxT>(k);
+            ta[slot] = IdxPair<IdxT>{d_sa[k - 1], static_cast<IdxT>(k)};
           }
         });
       }
       const unsigned pos_bits = round_up8(bit_length(n - 1));
-      const int where = radix_sort_pairs<uint64_t, IdxT>(st, eng.radix, pos_a.get(), rank_a.get(), pos_b.get(),
-                                                        rank_b.get(), m, 0, pos_bits);
-      const uint64_t* pos_i = where ? pos_b.get() : pos_a.get();
-      const IdxT* sa_rank = where ? rank_b.get() : rank_a.get();
+      const int where = radix_sort_pairs<IdxT, IdxPair<IdxT>>(st, eng.radix, pos_a.get(), tag_a.get(), pos_b.get(),
+                                                             tag_b.get(), m, 0, pos_bits);
+      const IdxT* pos_i = where ? pos_b.get() : pos_a.get();
+      const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
       plcp_for_pairs<IdxT>(
-          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return d_sa[sa_rank[t] - 1]; }, m,
-          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[sa_rank[t]] = lcp; });
+          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m,
+          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[tag[t].b] = lcp; });
     }
     clock.mark();  // 5
   }

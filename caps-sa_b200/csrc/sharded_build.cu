@@ -43,11 +43,6 @@ struct SliceMap {
   }
 };
 
-template <class IdxT>
-struct IdxPair {
-  IdxT a, b;
-};
-
 // ---- routing items to owner ranks ------------------------------------------------------
 // A route is a stable partition of m local items by destination rank (one counting pass of
 // the radix machinery on the destination as an 8-bit digit) plus the exchanged counts.
@@ -119,19 +114,36 @@ void route_backward(Engine& eng, Comm& comm, const Route<IdxT>& r, const T* answ
 }
 
 // ---- ranks sharded by text position ----------------------------------------------------
+// isa_local[pos - lo] = first SA position of suffix pos's group, for suffixes that have been
+// tied; everything else keeps the sentinel.  A lookup that hits the sentinel asks a second
+// owner: the rank whose bucket holds the suffix's (unique) key, which answers with the key's
+// global position (bucket offset + binary search in its sorted bucket).
 template <class IdxT>
 struct ShardedRanks {
   using Comp = typename IdxTraits<IdxT>::Comp;
+  static constexpr IdxT kUnset = ~IdxT(0);
   Engine& eng;
   Comm& comm;
   SliceMap map;
+  PackedText pt;
+  uint64_t key_mask;
+  const uint64_t* sorted_samples;  // pivot j = sorted_samples[(j + 1) * sample_stride - 1]
+  uint64_t sample_stride;
+  const uint64_t* bucket_keys;     // this rank's sorted bucket
+  uint64_t bucket_count, bucket_offset;
   uint64_t lo;              // first text position of this rank's slice
-  DevBuf<IdxT> isa_local;   // isa_local[pos - lo] = first SA position of suffix pos's group
+  DevBuf<IdxT> isa_local;
 
-  ShardedRanks(Engine& e, Comm& c, SliceMap m)
-      : eng(e), comm(c), map(m), lo(m.begin(static_cast<unsigned>(c.rank))) {
-    const uint64_t count = m.end(static_cast<unsigned>(c.rank)) - lo;
-    isa_local.alloc(count ? count : 1, e.stream);
+  ShardedRanks(Engine& e, Comm& c, SliceMap m, const PackedText& text, uint64_t mask, const uint64_t* samples,
+               uint64_t stride, const uint64_t* keys, uint64_t count, uint64_t offset)
+      : eng(e), comm(c), map(m), pt(text), key_mask(mask), sorted_samples(samples), sample_stride(stride),
+        bucket_keys(keys), bucket_count(count), bucket_offset(offset), lo(m.begin(static_cast<unsigned>(c.rank))) {
+    const uint64_t slice = m.end(static_cast<unsigned>(c.rank)) - lo;
+    isa_local.alloc(slice ? slice : 1, e.stream);
+  }
+
+  void reset() {
+    CAPSB_CUDA(cudaMemsetAsync(isa_local.get(), 0xFF, isa_local.size() * sizeof(IdxT), eng.stream));
   }
 
   bool any_active(uint64_t m) {
@@ -142,62 +154,106 @@ struct ShardedRanks {
     return false;
   }
 
-  // isa[idx(t)] = rank(t) on the rank that owns text position idx(t), for t in [0, m)
-  template <class IdxFn, class RankFn>
-  void publish_with(uint64_t m, IdxFn idx, RankFn rank_of) {
+  // isa[idx[t]] = head[t] on the rank that owns text position idx[t], for t in [0, m)
+  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
     const SliceMap mp = map;
-    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(idx(t)); });
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(idx[t]); });
     DevBuf<IdxPair<IdxT>> recv(rt.recv_total, eng.stream);
     route_forward<IdxPair<IdxT>>(
-        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{idx(t), rank_of(t)}; },
-        recv.get());
+        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{idx[t], head[t]}; }, recv.get());
     IdxT* isa = isa_local.get();
     const IdxPair<IdxT>* rv = recv.get();
     const uint64_t lo_ = lo;
     launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { isa[rv[j].a - lo_] = rv[j].b; });
   }
 
-  void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
-    publish_with(
-        m, [=] __device__(uint64_t t) -> IdxT { return idx[t]; }, [=] __device__(uint64_t t) -> IdxT { return head[t]; });
-  }
-
-  void publish_positions(const IdxT* sa, uint64_t count, uint64_t pos_base) {
-    publish_with(
-        count, [=] __device__(uint64_t k) -> IdxT { return sa[k]; },
-        [=] __device__(uint64_t k) -> IdxT { return static_cast<IdxT>(pos_base + k); });
-  }
-
   void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
     constexpr unsigned kField = IdxTraits<IdxT>::kField;
+    cudaStream_t st = eng.stream;
     const SliceMap mp = map;
     const uint64_t n = map.n, lo_ = lo;
     const unsigned self = static_cast<unsigned>(comm.rank);
-    // suffixes that run past the end need no rank; they ride along as a request to this rank
-    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned {
-      const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
-      return ih < n ? mp.owner(ih) : self;
-    });
-    DevBuf<IdxT> asked(rt.recv_total, eng.stream), answers(rt.recv_total, eng.stream);
-    route_forward<IdxT>(
-        eng, comm, rt,
-        [=] __device__(uint64_t t) -> IdxT {
-          const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
-          return static_cast<IdxT>(ih < n ? ih : lo_);
-        },
-        asked.get());
+    DevBuf<IdxT> second(m, st);
+    IdxT* sec = second.get();
+
+    // 1. ask the owner of text position i + h for its rank.  Suffixes that run past the end
+    //    need none; they ride along as a request to this rank.
     {
+      Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned {
+        const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
+        return ih < n ? mp.owner(ih) : self;
+      });
+      DevBuf<IdxT> asked(rt.recv_total, st), answers(rt.recv_total, st);
+      route_forward<IdxT>(
+          eng, comm, rt,
+          [=] __device__(uint64_t t) -> IdxT {
+            const uint64_t ih = static_cast<uint64_t>(idx[t]) + h;
+            return static_cast<IdxT>(ih < n ? ih : lo_);
+          },
+          asked.get());
       const IdxT* isa = isa_local.get();
       const IdxT* q = asked.get();
       IdxT* a = answers.get();
-      launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { a[j] = isa[q[j] - lo_]; });
+      launch_map(eng.dev, st, rt.recv_total, [=] __device__(uint64_t j) { a[j] = isa[q[j] - lo_]; });
+      route_backward<IdxT>(eng, comm, rt, answers.get(), [=] __device__(uint64_t t, IdxT r) { sec[t] = r; });
     }
-    route_backward<IdxT>(eng, comm, rt, answers.get(), [=] __device__(uint64_t t, IdxT rank_of_ih) {
+
+    // 2. never-tied suffixes: their rank is the global position of their key — ask the rank
+    //    whose bucket holds that key
+    {
+      auto unknown = [=] __device__(uint64_t t) -> IdxT {
+        return (static_cast<uint64_t>(idx[t]) + h < n && sec[t] == kUnset) ? IdxT(1) : IdxT(0);
+      };
+      const uint64_t pending = scan_total<IdxT, OpSum>(eng, m, unknown);
+      DevBuf<IdxT> slot_of(pending, st);
+      {
+        IdxT* so = slot_of.get();
+        scan_finish<IdxT, OpSum, false>(eng, m, unknown, [=] __device__(uint64_t t, IdxT j) {
+          if (static_cast<uint64_t>(idx[t]) + h < n && sec[t] == kUnset) so[j] = static_cast<IdxT>(t);
+        });
+      }
+      const IdxT* so = slot_of.get();
+      const PackedText text = pt;
+      const uint64_t mask = key_mask;
+      const uint64_t* samples = sorted_samples;
+      const uint64_t stride = sample_stride;
+      const unsigned pivots = static_cast<unsigned>(comm.world) - 1;
+      Route<IdxT> rt = plan_route<IdxT>(eng, comm, pending, [=] __device__(uint64_t j) -> unsigned {
+        const uint64_t key = text.window(static_cast<uint64_t>(idx[so[j]]) + h) & mask;
+        unsigned bucket = 0;  // number of pivots below the key (keys <= pivot j went to ranks <= j)
+        while (bucket < pivots && samples[static_cast<uint64_t>(bucket + 1) * stride - 1] < key) ++bucket;
+        return bucket;
+      });
+      DevBuf<uint64_t> asked(rt.recv_total, st);
+      DevBuf<IdxT> answers(rt.recv_total, st);
+      route_forward<uint64_t>(
+          eng, comm, rt,
+          [=] __device__(uint64_t j) -> uint64_t { return text.window(static_cast<uint64_t>(idx[so[j]]) + h) & mask; },
+          asked.get());
+      const uint64_t* keys = bucket_keys;
+      const uint64_t count = bucket_count, offset = bucket_offset;
+      const uint64_t* q = asked.get();
+      IdxT* a = answers.get();
+      launch_map(eng.dev, st, rt.recv_total, [=] __device__(uint64_t j) {
+        const uint64_t want = q[j];
+        uint64_t lo_k = 0, hi_k = count;
+        while (lo_k < hi_k) {
+          const uint64_t mid = (lo_k + hi_k) >> 1;
+          if (keys[mid] < want)
+            lo_k = mid + 1;
+          else
+            hi_k = mid;
+        }
+        a[j] = static_cast<IdxT>(offset + lo_k);
+      });
+      route_backward<IdxT>(eng, comm, rt, answers.get(), [=] __device__(uint64_t j, IdxT r) { sec[so[j]] = r; });
+    }
+
+    launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
       const uint64_t i = idx[t];
       const bool inside = i + h < n;
-      const uint64_t second = inside ? static_cast<uint64_t>(rank_of_ih) : (n - 1 - i);
-      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
-                static_cast<Comp>(second);
+      const uint64_t s2 = inside ? static_cast<uint64_t>(sec[t]) : (n - 1 - i);
+      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) | static_cast<Comp>(s2);
     });
   }
 };
@@ -362,8 +418,9 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     for (uint64_t v : all) any_ties = any_ties || v > 0;
   }
   if (any_ties) {
-    ShardedRanks<IdxT> ranks(eng, comm, map);
-    refine_tied_groups<IdxT>(eng, ranks, keys, d_sa, bucket_count, bucket_offset, n, key_bits >> log2_bits);
+    ShardedRanks<IdxT> ranks(eng, comm, map, pt, key_mask_of(key_bits), sorted_samples, kSamplesPerRank, keys,
+                             bucket_count, bucket_offset);
+    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, bucket_count, bucket_offset, n);
   }
   clock.mark("ties resolved");  // 5
 
@@ -416,29 +473,29 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     route_forward<IdxPair<IdxT>>(
         eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{pi[t], pj[t]}; }, recv.get());
 
-    // order the received pairs by text position so the permuted-LCP chains are contiguous
-    DevBuf<uint64_t> pos_a(got, st), pos_b(got, st);
-    DevBuf<IdxT> slot_a(got, st), slot_b(got, st), answers(got, st);
+    // order the received pairs by text position so the permuted-LCP chains are contiguous;
+    // the predecessor j and the arrival slot travel with the position as the sort's value
+    DevBuf<IdxT> pos_a(got, st), pos_b(got, st), answers(got, st);
+    DevBuf<IdxPair<IdxT>> tag_a(got, st), tag_b(got, st);
     {
       const IdxPair<IdxT>* rv = recv.get();
-      uint64_t* pa = pos_a.get();
-      IdxT* sa_ = slot_a.get();
+      IdxT* pa = pos_a.get();
+      IdxPair<IdxT>* ta = tag_a.get();
       launch_map(dev, st, got, [=] __device__(uint64_t j) {
         pa[j] = rv[j].a;
-        sa_[j] = static_cast<IdxT>(j);
+        ta[j] = IdxPair<IdxT>{rv[j].b, static_cast<IdxT>(j)};
       });
     }
     const unsigned pos_bits = round_up8(bit_length(n - 1));
-    const int where = radix_sort_pairs<uint64_t, IdxT>(st, eng.radix, pos_a.get(), slot_a.get(), pos_b.get(),
-                                                      slot_b.get(), got, 0, pos_bits);
-    const uint64_t* pos_i = where ? pos_b.get() : pos_a.get();
-    const IdxT* slot = where ? slot_b.get() : slot_a.get();
+    const int where = radix_sort_pairs<IdxT, IdxPair<IdxT>>(st, eng.radix, pos_a.get(), tag_a.get(), pos_b.get(),
+                                                           tag_b.get(), got, 0, pos_bits);
+    const IdxT* pos_i = where ? pos_b.get() : pos_a.get();
+    const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
     {
-      const IdxPair<IdxT>* rv = recv.get();
       IdxT* ans = answers.get();
       plcp_for_pairs<IdxT>(
-          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return rv[slot[t]].b; }, got,
-          [=] __device__(uint64_t t, IdxT lcp) { ans[slot[t]] = lcp; });
+          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, got,
+          [=] __device__(uint64_t t, IdxT lcp) { ans[tag[t].b] = lcp; });
     }
     route_backward<IdxT>(eng, comm, rt, answers.get(),
                          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[pk[t]] = lcp; });
