@@ -50,7 +50,8 @@ class Stats(C.Structure):
                 ("ms_h2d", C.c_float), ("ms_d2h", C.c_float), ("scatter_launches", C.c_uint32),
                 ("ms_scatter", C.c_float), ("scatter_bytes", C.c_uint64), ("key_bits", C.c_uint32),
                 ("reserved", C.c_uint32), ("ms_partition", C.c_float), ("ms_merge", C.c_float),
-                ("comm_bytes", C.c_uint64), ("shard_offset", C.c_uint64), ("shard_count", C.c_uint64)]
+                ("comm_bytes", C.c_uint64), ("shard_offset", C.c_uint64), ("shard_count", C.c_uint64),
+                ("pairs_chained", C.c_uint64)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}

@@ -131,6 +131,7 @@ void fill_stats(const capsb::Stats& s, caps_sa_gpu_stats* out) {
   out->ms_partition = s.ms_partition, out->ms_merge = s.ms_merge;
   out->comm_bytes = s.comm_bytes;
   out->shard_offset = s.shard_offset, out->shard_count = s.shard_count;
+  out->pairs_chained = s.pairs_chained;
 }
 
 template <class IdxT>

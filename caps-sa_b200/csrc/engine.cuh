@@ -36,6 +36,7 @@ struct Stats {
   uint64_t comm_bytes = 0;    // bytes this rank moved to other ranks
   uint64_t shard_offset = 0;  // this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count)
   uint64_t shard_count = 0;
+  uint64_t pairs_chained = 0;  // groups of two finished by the pair-chain step
 };
 
 struct PackedTextBuf {

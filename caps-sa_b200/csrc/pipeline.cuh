@@ -40,6 +40,13 @@ struct IdxPair {
   IdxT a, b;
 };
 
+template <class IdxT>
+void chain_pairs_local(Engine& eng, const PackedText& pt, IdxT* hi, const IdxT* lo, uint64_t m, uint64_t known,
+                       IdxPair<IdxT>* answer);
+template <class IdxT, class PosJ, class Out>
+void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ pos_j, uint64_t m, uint64_t known,
+                    Out out);
+
 inline unsigned bit_length(uint64_t v) {
   unsigned b = 0;
   while (v) ++b, v >>= 1;
@@ -206,6 +213,11 @@ struct LocalRanks {
     launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) { d_isa[idx[t]] = head[t]; });
   }
 
+  // answer[j] = {lcp, hi sorts first} for the pairs (lo[j], hi[j]); see chain_pairs_local
+  void chain_pairs(IdxT* hi, const IdxT* lo, uint64_t m, uint64_t known, IdxPair<IdxT>* answer) {
+    chain_pairs_local<IdxT>(eng, pt, hi, lo, m, known, answer);
+  }
+
   // comp[t] = (group[t] + inside) << field | second, where second is the rank of suffix
   // idx[t] + h, or n - 1 - idx[t] beyond the end (shorter suffix first = larger position first)
   void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
@@ -251,6 +263,10 @@ struct LocalRanks {
 // ---------------------------------------------------------------------------------------
 constexpr unsigned kSmallGroup = 32;  // groups up to this size are ordered by counting, not sorting
 
+// d_lcp value of a position whose LCP is still to be computed (an LCP is at most n - 1)
+template <class IdxT>
+constexpr IdxT kLcpUnset = ~IdxT(0);
+
 // The suffixes still being ordered, in SA order; the members of a group are consecutive.
 template <class IdxT>
 struct ActiveList {
@@ -259,6 +275,135 @@ struct ActiveList {
   DevBuf<IdxT> idx;    // suffix (text position)
   DevBuf<IdxT> group;  // global SA position of the group's first member
 };
+
+// ---------------------------------------------------------------------------------------
+// Groups of exactly two suffixes {lo < hi} are finished in one step instead of riding through
+// the doubling rounds (an exact duplicate of length L keeps ~L pairs tied for log2(L) rounds):
+// the pair is compared directly.  What keeps that linear is the permuted-LCP chain rule applied
+// before the order is known: if (lo - 1, hi - 1) is also a group of two, then
+// lcp(lo, hi) = lcp(lo - 1, hi - 1) - 1 and the two pairs are ordered the same way, so only the
+// first pair of a chain of consecutive text positions is compared (plcp_for_pairs); the rest
+// inherit.  The LCP of the pair falls out as well, so these positions skip the deep-LCP stage.
+//
+// chain_pairs_local: answer[j] = {lcp(lo_j, hi_j), 1 if suffix hi_j sorts first else 0} for m
+// pairs in any order.  hi[] is overwritten (used as sort buffer).
+// ---------------------------------------------------------------------------------------
+template <class IdxT>
+void chain_pairs_local(Engine& eng, const PackedText& pt, IdxT* hi, const IdxT* lo, uint64_t m, uint64_t known,
+                       IdxPair<IdxT>* answer) {
+  if (m == 0) return;
+  cudaStream_t st = eng.stream;
+  DevBuf<IdxT> pos_b(m, st);
+  DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
+  {
+    IdxPair<IdxT>* ta = tag_a.get();
+    launch_map(eng.dev, st, m, [=] __device__(uint64_t j) { ta[j] = IdxPair<IdxT>{lo[j], static_cast<IdxT>(j)}; });
+  }
+  const unsigned pos_bits = round_up8(bit_length(pt.n - 1));
+  const int where = radix_sort_pairs<IdxT, IdxPair<IdxT>>(st, eng.radix, hi, tag_a.get(), pos_b.get(), tag_b.get(), m,
+                                                         0, pos_bits);
+  const IdxT* pos_i = where ? pos_b.get() : hi;
+  const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
+  plcp_for_pairs<IdxT>(
+      eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m, known,
+      [=] __device__(uint64_t t, IdxT lcp, uint64_t head, IdxT head_lcp) {
+        // the order of the chain's first pair decides the whole chain
+        const uint64_t a = tag[head].a, b = pos_i[head];  // a < b
+        const uint64_t l = head_lcp;
+        const bool hi_first = (b + l >= pt.n) ? true : pt.symbol(b + l) < pt.symbol(a + l);
+        answer[tag[t].b] = IdxPair<IdxT>{lcp, static_cast<IdxT>(hi_first ? 1 : 0)};
+      });
+}
+
+// Finishes every group of two in the active list: final order into d_sa, their LCP into d_lcp,
+// ranks published, and the pairs leave the list.  Collective in the sharded path (the pairs
+// travel to the rank that owns text position hi, where the chains are contiguous).
+template <class IdxT, class Ranks>
+void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa, IdxT* d_lcp, uint64_t pos_base,
+                   uint64_t known) {
+  cudaStream_t st = eng.stream;
+  const uint64_t m = act.m;
+  const IdxT* p = act.pos.get();
+  const IdxT* s = act.idx.get();
+  const IdxT* g = act.group.get();
+  auto pair_first = [=] __device__(uint64_t t) -> IdxT {
+    const IdxT grp = g[t];
+    const bool first = static_cast<uint64_t>(p[t]) + pos_base == static_cast<uint64_t>(grp);
+    return (first && t + 1 < m && g[t + 1] == grp && (t + 2 >= m || g[t + 2] != grp)) ? IdxT(1) : IdxT(0);
+  };
+  const uint64_t pairs = scan_total<IdxT, OpSum>(eng, m, pair_first);
+  eng.stats.pairs_chained += pairs;
+  DevBuf<IdxT> hi(pairs, st), lo(pairs, st), slot(pairs, st);
+  DevBuf<IdxPair<IdxT>> answer(pairs, st);
+  if (pairs > 0) {
+    IdxT* h = hi.get();
+    IdxT* l = lo.get();
+    IdxT* sl = slot.get();
+    scan_finish<IdxT, OpSum, false>(eng, m, pair_first, [=] __device__(uint64_t t, IdxT j) {
+      const IdxT grp = g[t];
+      const bool first = static_cast<uint64_t>(p[t]) + pos_base == static_cast<uint64_t>(grp);
+      if (first && t + 1 < m && g[t + 1] == grp && (t + 2 >= m || g[t + 2] != grp)) {
+        const IdxT a = s[t], b = s[t + 1];
+        h[j] = a > b ? a : b;
+        l[j] = a > b ? b : a;
+        sl[j] = static_cast<IdxT>(t);
+      }
+    });
+  }
+  ranks.chain_pairs(hi.get(), lo.get(), pairs, known, answer.get());
+  DevBuf<IdxT> pub_idx(2 * pairs, st), pub_head(2 * pairs, st);
+  if (pairs > 0) {
+    const IdxT* l = lo.get();
+    const IdxT* sl = slot.get();
+    const IdxPair<IdxT>* ans = answer.get();
+    IdxT* pi = pub_idx.get();
+    IdxT* ph = pub_head.get();
+    // hi[] was consumed by the sort: the larger position is the pair's other member
+    launch_map(eng.dev, st, pairs, [=] __device__(uint64_t j) {
+      const uint64_t t = sl[j];
+      const IdxT a = s[t], b = s[t + 1];
+      const IdxT low = l[j], high = a == low ? b : a;
+      const bool hi_first = ans[j].b != 0;
+      const uint64_t k = p[t];
+      const IdxT small = hi_first ? high : low, large = hi_first ? low : high;
+      d_sa[k] = small;
+      d_sa[k + 1] = large;
+      d_lcp[k + 1] = ans[j].a;
+      pi[2 * j] = small, ph[2 * j] = static_cast<IdxT>(pos_base + k);
+      pi[2 * j + 1] = large, ph[2 * j + 1] = static_cast<IdxT>(pos_base + k + 1);
+    });
+  }
+  ranks.publish(pub_idx.get(), pub_head.get(), 2 * pairs);
+
+  if (pairs == 0) return;
+  auto stays = [=] __device__(uint64_t t) -> IdxT {
+    const IdxT grp = g[t];
+    const uint64_t first = t - (static_cast<uint64_t>(p[t]) + pos_base - static_cast<uint64_t>(grp));
+    const bool pair = first + 1 < m && g[first + 1] == grp && (first + 2 >= m || g[first + 2] != grp);
+    return pair ? IdxT(0) : IdxT(1);
+  };
+  const uint64_t m_next = m - 2 * pairs;
+  DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
+  if (m_next > 0) {
+    IdxT* np = n_pos.get();
+    IdxT* ns = n_idx.get();
+    IdxT* ngp = n_group.get();
+    scan_full<IdxT, OpSum, false>(eng, m, stays, [=] __device__(uint64_t t, IdxT out) {
+      const IdxT grp = g[t];
+      const uint64_t first = t - (static_cast<uint64_t>(p[t]) + pos_base - static_cast<uint64_t>(grp));
+      const bool pair = first + 1 < m && g[first + 1] == grp && (first + 2 >= m || g[first + 2] != grp);
+      if (!pair) {
+        np[out] = p[t];
+        ns[out] = s[t];
+        ngp[out] = grp;
+      }
+    });
+  }
+  act.pos = std::move(n_pos);
+  act.idx = std::move(n_idx);
+  act.group = std::move(n_group);
+  act.m = m_next;
+}
 
 // One refinement round on the active list.  comp_a[t] = group field (the group head plus one
 // for suffixes that reach depth h inside the text) above a `second` field whose bits
@@ -420,7 +565,7 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
 // ---------------------------------------------------------------------------------------
 template <class IdxT, class Ranks>
 void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
-                        IdxT* d_sa, uint64_t count, uint64_t pos_base, uint64_t n) {
+                        IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n) {
   using Comp = typename IdxTraits<IdxT>::Comp;
   constexpr unsigned kField = IdxTraits<IdxT>::kField;
   using Wide = unsigned __int128;
@@ -447,6 +592,8 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
       if (tied) {
         p[slot] = static_cast<IdxT>(k);
         s[slot] = d_sa[k];
+        // LCP with a tied predecessor: unknown until the pair-chain step or the deep-LCP stage
+        if (k > 0 && keys[k] == keys[k - 1]) d_lcp[k] = kLcpUnset<IdxT>;
       }
     });
     // group head (global SA position) of every active suffix: running maximum of the heads
@@ -471,6 +618,14 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
   }
   bool first_round = true;
   while (ranks.any_active(act.m)) {
+    // groups of two are finished directly (order and LCP); the rest goes through a doubling round
+    resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h);
+    if (trace) {
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      std::fprintf(stderr, "[capsb] pairs finished so far: %llu, active now %llu\n",
+                   (unsigned long long)eng.stats.pairs_chained, (unsigned long long)act.m);
+    }
+    if (!ranks.any_active(act.m)) break;
     eng.stats.refine_rounds++;
     if (trace) round_start = std::chrono::steady_clock::now();
     const uint64_t m = act.m;
@@ -589,9 +744,12 @@ __global__ void __launch_bounds__(256) long_lcp_kernel(PackedText pt, const IdxT
 // pair (i_t - 1, j_t - 1) is pair t-1 of the list and the preceding symbols agree; then
 // LCP_t = LCP_{t-1} - 1 (Karkkainen-Manzini-Puglisi).  Irreducible pairs are compared
 // directly: 16 packed words per thread, then one CTA per pair for the rare long ones.
-// out(t, lcp) is called once per pair.
+// `known` symbols are known to agree for every pair (when both suffixes are that long).
+// out(t, lcp, head, head_lcp) is called once per pair; head is the list index of the irreducible
+// pair its chain starts at and head_lcp that pair's LCP.
 template <class IdxT, class PosJ, class Out>
-void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ pos_j, uint64_t m, Out out) {
+void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ pos_j, uint64_t m, uint64_t known,
+                    Out out) {
   if (m == 0) return;
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
@@ -613,7 +771,7 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ p
       ch[t] = chained ? IdxT(0) : static_cast<IdxT>(t);
       if (!chained) {
         uint64_t l = 0;
-        const bool done = pt.common_prefix(i, j, 0, 16, &l);
+        const bool done = pt.common_prefix(i, j, known, 16, &l);
         pl[t] = static_cast<IdxT>(l);
         atomicAdd(cnt + 0, 1ull);
         if (!done) td[atomicAdd(cnt + 1, 1ull)] = static_cast<IdxT>(t);
@@ -638,7 +796,7 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ p
         eng, m, [=] __device__(uint64_t t) -> IdxT { return ch[t]; },
         [=] __device__(uint64_t t, IdxT head) {
           const uint64_t back = static_cast<uint64_t>(pos_i[t]) - static_cast<uint64_t>(pos_i[head]);
-          out(t, static_cast<IdxT>(static_cast<uint64_t>(pl[head]) - back));
+          out(t, static_cast<IdxT>(static_cast<uint64_t>(pl[head]) - back), static_cast<uint64_t>(head), pl[head]);
         });
   }
 }

@@ -4,8 +4,8 @@
 // chunk of the input (so a pass needs no inter-CTA waiting and cannot hang):
 //   radix_hist_kernel     per-CTA digit histogram                 -> hist[digit][cta]
 //   radix_offsets_kernel  (256 CTAs) exclusive scan of each digit row + digit totals
-//   radix_scatter_kernel  re-reads the chunk tile by tile, ranks the tile's keys with
-//                         warp match_any (stable), and scatters keys + values
+//   radix_scatter_kernel  re-reads the chunk tile by tile, ranks the tile's keys inside each
+//                         warp (stable), and scatters keys + values
 // HBM traffic per pass: keys twice + values once in, keys + values once out.
 //
 // Keys come from a `Src` functor, so the first pass of the suffix sort reads the packed
@@ -22,10 +22,9 @@ namespace capsb {
 
 constexpr int kRadixBits = 8;
 constexpr int kRadixSize = 1 << kRadixBits;
-constexpr int kRsThreads = 256;
+constexpr int kRsThreads = 256;         // histogram kernel
 constexpr int kRsWarps = kRsThreads / 32;
-constexpr int kRsItems = 16;
-constexpr int kRsTile = kRsThreads * kRsItems;
+constexpr int kRsTile = 4096;           // scatter tile (every layout: threads x items = 4096); chunks are multiples
 
 template <class KeyT>
 __device__ __forceinline__ unsigned radix_digit(KeyT key, unsigned shift) {
@@ -79,55 +78,108 @@ static __global__ void __launch_bounds__(kScanThreads) radix_offsets_kernel(uint
   if (threadIdx.x == 0) digit_total[blockIdx.x] = carry;
 }
 
-// Shared-memory layout of the scatter kernel.  The staging area holds the tile in
-// digit-sorted order: first the keys, then (reusing the same bytes) the values.
+// ---------------------------------------------------------------------------------------
+// Scatter kernel.  A CTA of kThreads threads walks its chunk in tiles of kThreads * kItems
+// elements.  Per tile:
+//   1. coalesced key loads (warp-striped: (warp, item, lane) lexicographic == input order),
+//      value loads issued right behind them so their latency hides under the ranking;
+//   2. stable in-warp ranking: every lane ORs its lane bit into the warp's per-digit mask word
+//      in shared memory and reads the word back (= the lanes of this row that hold the same
+//      digit); the lowest such lane adds the row's count to the warp's digit counter.
+//      (~15 instructions per row; MATCH.ANY saturates the XU pipe and a ballot per digit bit
+//      costs ~50 — profiles/r01/README.md.)  kRsMatchSlots rows are in flight together;
+//   3. digit d: exclusive scan over the warps, digit starts inside the tile, global shifts;
+//   4. keys and values are placed in digit-sorted order in shared memory (separate staging
+//      areas when they fit, else the values reuse the key bytes);
+//   5. consecutive threads write consecutive staged elements: only whole digit runs leave the
+//      SM, so HBM sees ~1x the algorithmic write traffic.
+// Occupancy is bounded by the register file (64 K registers per SM): kItems = 8 with 512
+// threads keeps the 4096-element tile (16-element digit runs on average) at 64 registers per
+// thread, i.e. 32 resident warps per SM instead of the 16 of a 256 x 16 layout (ncu of that
+// layout: warps active 25 %, stalls spread over barrier / long / short scoreboard, DRAM 41 %).
+// ---------------------------------------------------------------------------------------
 constexpr int kRsMatchSlots = 2;  // rows of a warp whose peer masks are in flight together
-template <class KeyT, class ValT>
-struct ScatterSmem {
-  union Stage {
-    KeyT keys[kRsTile];
-    ValT vals[kRsTile];
-  } stage;
-  uint64_t run_base[kRadixSize];    // next free global slot per digit for this CTA
-  uint64_t out_shift[kRadixSize];   // global slot of tile-sorted position s is out_shift[digit] + s
-  unsigned digit_start[kRadixSize]; // first tile-sorted position of each digit
-  unsigned warp_cnt[kRsWarps][kRadixSize + 1];  // [..][256] collects out-of-range lanes
-  unsigned match[kRsWarps][kRsMatchSlots][kRadixSize + 1];  // lanes of the warp holding each digit (one row)
-  uint64_t scan_tmp[kScanThreads / 32];
+
+template <class KeyT, class ValT, int kThreads, int kItems>
+struct ScatterCfg {
+  static constexpr int kWarps = kThreads / 32;
+  static constexpr int kTile = kThreads * kItems;
+  // both staging areas at once if that keeps two CTAs of this layout resident on an SM
+  static constexpr bool kSeparate = (sizeof(KeyT) + sizeof(ValT)) * kTile <= 56 * 1024;
 };
 
-// One tile of the scatter pass.  kFull = the tile has all kRsTile elements (no bounds checks).
-//
-// Ranking: every lane ORs its lane bit into the warp's per-digit mask word in shared memory,
-// reads the word back (= the lanes of this row that hold the same digit), and the lowest such
-// lane adds the row's count to the warp's digit counter.  That is ~15 instructions per row
-// where a ballot per digit bit costs ~50 and MATCH.ANY saturates the XU pipe
-// (profiles/r01/README.md).  Two rows are in flight at a time (kRsMatchSlots).
-template <bool kFull, class KeyT, class ValT, class Src>
-__device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT>& sm, const Src& src, uint64_t tile, unsigned valid,
-                                             unsigned shift, KeyT* __restrict__ keys_out,
-                                             ValT* __restrict__ vals_out) {
+template <class KeyT, class ValT, int kThreads, int kItems>
+struct ScatterSmem {
+  using Cfg = ScatterCfg<KeyT, ValT, kThreads, kItems>;
+  static constexpr size_t kStageBytes =
+      Cfg::kSeparate ? (sizeof(KeyT) + sizeof(ValT)) * Cfg::kTile
+                     : (sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT)) * Cfg::kTile;
+  alignas(16) unsigned char stage[kStageBytes];
+  uint64_t run_base[kRadixSize];     // next free global slot per digit for this CTA
+  uint64_t out_shift[kRadixSize];    // global slot of tile-sorted position s is out_shift[digit] + s
+  unsigned digit_start[kRadixSize];  // first tile-sorted position of each digit
+  unsigned warp_cnt[Cfg::kWarps][kRadixSize + 1];  // [..][256] collects out-of-range lanes
+  unsigned match[Cfg::kWarps][kRsMatchSlots][kRadixSize + 1];  // lanes of the warp holding each digit (one row)
+  uint64_t scan_tmp[8];
+  __device__ __forceinline__ KeyT* keys() { return reinterpret_cast<KeyT*>(stage); }
+  __device__ __forceinline__ ValT* vals() {
+    return reinterpret_cast<ValT*>(stage + (Cfg::kSeparate ? sizeof(KeyT) * Cfg::kTile : 0));
+  }
+};
+
+// Exclusive sum over the 256 digits (threads 0..255 contribute `v`; called by every thread).
+template <int kThreads>
+__device__ __forceinline__ uint64_t digit_scan(uint64_t v, uint64_t* smem /*[8]*/) {
+  const unsigned tid = threadIdx.x;
+  const unsigned warp = tid >> 5;
+  uint64_t inc = 0;
+  if (tid < kRadixSize) {
+    inc = warp_scan_inclusive<uint64_t, OpSum>(v);
+    if ((tid & 31u) == 31u) smem[warp] = inc;
+  }
+  __syncthreads();
+  uint64_t prefix = 0;
+#pragma unroll
+  for (int w = 0; w < kRadixSize / 32; ++w)
+    if (static_cast<unsigned>(w) < warp) prefix += smem[w];
+  return prefix + inc - v;
+}
+
+// One tile of the scatter pass.  kFull = the tile has all kTile elements (no bounds checks).
+template <bool kFull, class KeyT, class ValT, class Src, int kThreads, int kItems>
+__device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, kItems>& sm, const Src& src,
+                                             uint64_t tile, unsigned valid, unsigned shift,
+                                             KeyT* __restrict__ keys_out, ValT* __restrict__ vals_out) {
+  using Cfg = ScatterCfg<KeyT, ValT, kThreads, kItems>;
+  constexpr int kWarps = Cfg::kWarps;
+  constexpr bool kEarlyVals = Cfg::kSeparate && sizeof(ValT) <= 8;
   const unsigned tid = threadIdx.x;
   const unsigned lane = tid & 31u;
   const unsigned warp = tid >> 5;
   const unsigned lt = lanemask_lt();
   const unsigned lane_bit = 1u << lane;
 
-  for (int i = tid; i < kRsWarps * (kRadixSize + 1); i += kRsThreads) (&sm.warp_cnt[0][0])[i] = 0;
+  for (int i = tid; i < kWarps * (kRadixSize + 1); i += kThreads) (&sm.warp_cnt[0][0])[i] = 0;
   __syncthreads();  // also orders the previous tile's shared-memory reads before new writes
 
-  // warp-striped layout keeps global loads coalesced and defines the stable order:
-  // (warp, item, lane) lexicographic == increasing input index.
-  const unsigned warp_first = warp * (32 * kRsItems) + lane;
-  KeyT key[kRsItems];
-  unsigned slot[kRsItems];  // rank among equal digits of the warp -> tile-sorted position
+  const unsigned warp_first = warp * (32 * kItems) + lane;
+  KeyT key[kItems];
+  ValT val[kItems];
+  unsigned slot[kItems];  // rank among equal digits of the warp -> tile-sorted position
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t) {
+  for (int t = 0; t < kItems; ++t) {
     const unsigned off = warp_first + t * 32;
     key[t] = (kFull || off < valid) ? src.key(tile + off) : KeyT(0);
   }
+  if (kEarlyVals) {
 #pragma unroll
-  for (int t0 = 0; t0 < kRsItems; t0 += kRsMatchSlots) {
+    for (int t = 0; t < kItems; ++t) {
+      const unsigned off = warp_first + t * 32;
+      val[t] = (kFull || off < valid) ? src.val(tile + off) : ValT{};
+    }
+  }
+#pragma unroll
+  for (int t0 = 0; t0 < kItems; t0 += kRsMatchSlots) {
     unsigned d[kRsMatchSlots];
 #pragma unroll
     for (int u = 0; u < kRsMatchSlots; ++u) {
@@ -158,104 +210,113 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT>& sm, const 
 
   {  // digit `tid`: exclusive scan over warps, digit starts inside the tile, global shifts
     unsigned run = 0;
+    if (tid < kRadixSize) {
 #pragma unroll
-    for (int w = 0; w < kRsWarps; ++w) {
-      const unsigned c = sm.warp_cnt[w][tid];
-      sm.warp_cnt[w][tid] = run;
-      run += c;
+      for (int w = 0; w < kWarps; ++w) {
+        const unsigned c = sm.warp_cnt[w][tid];
+        sm.warp_cnt[w][tid] = run;
+        run += c;
+      }
     }
-    uint64_t inc, total;
-    const uint64_t start = block_scan<uint64_t, OpSum>(static_cast<uint64_t>(run), &inc, &total, sm.scan_tmp);
-    const uint64_t base = sm.run_base[tid];
-    sm.digit_start[tid] = static_cast<unsigned>(start);
-    sm.out_shift[tid] = base - start;  // modular arithmetic: out_shift + s is exact
-    sm.run_base[tid] = base + run;
+    const uint64_t start = digit_scan<kThreads>(static_cast<uint64_t>(run), sm.scan_tmp);
+    if (tid < kRadixSize) {
+      const uint64_t base = sm.run_base[tid];
+      sm.digit_start[tid] = static_cast<unsigned>(start);
+      sm.out_shift[tid] = base - start;  // modular arithmetic: out_shift + s is exact
+      sm.run_base[tid] = base + run;
+    }
   }
   __syncthreads();
 
+  KeyT* stage_keys = sm.keys();
+  ValT* stage_vals = sm.vals();
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t) {
+  for (int t = 0; t < kItems; ++t) {
     if (kFull || warp_first + t * 32 < valid) {
       const unsigned d = radix_digit<KeyT>(key[t], shift);
       slot[t] += sm.digit_start[d] + sm.warp_cnt[warp][d];
-      sm.stage.keys[slot[t]] = key[t];
+      stage_keys[slot[t]] = key[t];
+      if (kEarlyVals) stage_vals[slot[t]] = val[t];
     }
   }
-  // the values are needed only after the keys have left; issue their loads now
-  ValT val[kRsItems];
+  if (!kEarlyVals) {  // the values are needed only after the keys have left; issue their loads now
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t) {
-    const unsigned off = warp_first + t * 32;
-    val[t] = (kFull || off < valid) ? src.val(tile + off) : ValT{};
+    for (int t = 0; t < kItems; ++t) {
+      const unsigned off = warp_first + t * 32;
+      val[t] = (kFull || off < valid) ? src.val(tile + off) : ValT{};
+    }
   }
   __syncthreads();
 
-  unsigned digits[kRsItems / 4];  // digit of tile-sorted position t*256+tid, 8 bits each
+  unsigned digits[(kItems + 3) / 4];  // digit of tile-sorted position t*kThreads+tid, 8 bits each
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t) {
-    const unsigned s = static_cast<unsigned>(t) * kRsThreads + tid;
+  for (int t = 0; t < kItems; ++t) {
+    const unsigned s = static_cast<unsigned>(t) * kThreads + tid;
     if ((t & 3) == 0) digits[t >> 2] = 0;
     if (kFull || s < valid) {
-      const KeyT k = sm.stage.keys[s];
+      const KeyT k = stage_keys[s];
       const unsigned d = radix_digit<KeyT>(k, shift);
       digits[t >> 2] |= d << (8 * (t & 3));
 #ifdef CAPSB_RADIX_EXPERIMENT_SEQ_WRITE  // tools/radix_bench.cu only: timing without the scatter pattern
       keys_out[tile + s] = k;
+      if (kEarlyVals) vals_out[tile + s] = stage_vals[s];
 #else
-      keys_out[sm.out_shift[d] + s] = k;
+      const uint64_t g = sm.out_shift[d] + s;
+      keys_out[g] = k;
+      if (kEarlyVals) vals_out[g] = stage_vals[s];
 #endif
     }
   }
-  __syncthreads();  // every key has been read; the staging bytes now take the values
-
+  if (!kEarlyVals) {
+    if (!Cfg::kSeparate) __syncthreads();  // every key has been read; the staging bytes now take the values
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t)
-    if (kFull || warp_first + t * 32 < valid) sm.stage.vals[slot[t]] = val[t];
-  __syncthreads();
+    for (int t = 0; t < kItems; ++t)
+      if (kFull || warp_first + t * 32 < valid) stage_vals[slot[t]] = val[t];
+    __syncthreads();
 #pragma unroll
-  for (int t = 0; t < kRsItems; ++t) {
-    const unsigned s = static_cast<unsigned>(t) * kRsThreads + tid;
-    if (kFull || s < valid) {
-      const unsigned d = (digits[t >> 2] >> (8 * (t & 3))) & 0xFFu;
+    for (int t = 0; t < kItems; ++t) {
+      const unsigned s = static_cast<unsigned>(t) * kThreads + tid;
+      if (kFull || s < valid) {
+        const unsigned d = (digits[t >> 2] >> (8 * (t & 3))) & 0xFFu;
 #ifdef CAPSB_RADIX_EXPERIMENT_SEQ_WRITE
-      vals_out[tile + s] = sm.stage.vals[s] + d;
+        vals_out[tile + s] = stage_vals[s];
 #else
-      vals_out[sm.out_shift[d] + s] = sm.stage.vals[s];
+        vals_out[sm.out_shift[d] + s] = stage_vals[s];
 #endif
+      }
     }
   }
 }
 
-// Tile pipeline: coalesced key loads -> stable in-tile ranking -> keys reordered by digit in
-// shared memory -> coalesced runs written to each digit's global range -> the same for the
-// values through the same staging bytes.  Only full sectors leave the SM except at run
-// boundaries, so HBM sees ~1x the algorithmic write traffic.
-template <class KeyT, class ValT, class Src, int kMinBlocks>
-__global__ void __launch_bounds__(kRsThreads, kMinBlocks) radix_scatter_kernel(Src src, uint64_t n, uint64_t chunk,
-                                                                      unsigned shift,
-                                                                      const uint64_t* __restrict__ hist,
-                                                                      const uint64_t* __restrict__ digit_total,
-                                                                      KeyT* __restrict__ keys_out,
-                                                                      ValT* __restrict__ vals_out) {
+template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src src, uint64_t n, uint64_t chunk,
+                                                                    unsigned shift,
+                                                                    const uint64_t* __restrict__ hist,
+                                                                    const uint64_t* __restrict__ digit_total,
+                                                                    KeyT* __restrict__ keys_out,
+                                                                    ValT* __restrict__ vals_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ScatterSmem<KeyT, ValT>& sm = *reinterpret_cast<ScatterSmem<KeyT, ValT>*>(smem_raw);
+  using Smem = ScatterSmem<KeyT, ValT, kThreads, kItems>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
+  constexpr int kTile = kThreads * kItems;
   const unsigned tid = threadIdx.x;
 
   {  // global base of digit d = sum of totals of smaller digits; plus this CTA's row offset
-    const uint64_t t = digit_total[tid];
-    uint64_t inc, total;
-    const uint64_t excl = block_scan<uint64_t, OpSum>(t, &inc, &total, sm.scan_tmp);
-    sm.run_base[tid] = excl + hist[static_cast<uint64_t>(tid) * gridDim.x + blockIdx.x];
+    const uint64_t t = tid < kRadixSize ? digit_total[tid] : 0;
+    const uint64_t excl = digit_scan<kThreads>(t, sm.scan_tmp);
+    if (tid < kRadixSize) sm.run_base[tid] = excl + hist[static_cast<uint64_t>(tid) * gridDim.x + blockIdx.x];
   }
-  for (int i = tid; i < kRsWarps * kRsMatchSlots * (kRadixSize + 1); i += kRsThreads) (&sm.match[0][0][0])[i] = 0;
+  for (int i = tid; i < (kThreads / 32) * kRsMatchSlots * (kRadixSize + 1); i += kThreads)
+    (&sm.match[0][0][0])[i] = 0;
 
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
   uint64_t tile = begin;
-  for (; tile + kRsTile <= end; tile += kRsTile)
-    scatter_tile<true, KeyT, ValT, Src>(sm, src, tile, kRsTile, shift, keys_out, vals_out);
+  for (; tile + kTile <= end; tile += kTile)
+    scatter_tile<true, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, kTile, shift, keys_out, vals_out);
   if (tile < end)
-    scatter_tile<false, KeyT, ValT, Src>(sm, src, tile, static_cast<unsigned>(end - tile), shift, keys_out, vals_out);
+    scatter_tile<false, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, static_cast<unsigned>(end - tile), shift,
+                                                          keys_out, vals_out);
 }
 
 // Host driver ---------------------------------------------------------------------------
@@ -304,13 +365,13 @@ struct RadixScratch {
   DevBuf<uint64_t> hist;         // [256][blocks]
   DevBuf<uint64_t> digit_total;  // [256]
   unsigned max_blocks = 0;
-  int min_blocks = 2;  // resident scatter CTAs per SM the kernel is compiled for (measured best: profiles/r01)
+  int variant = 1;  // scatter layout: 0 = 256 threads x 16 items, 1 = 512 x 8 (default; measured: profiles/r01)
   int device = 0;
   KernelTimer timer;
   void init(const DeviceInfo& dev, cudaStream_t stream) {
     device = dev.device;
-    if (const char* env = std::getenv("CAPSB_SCATTER_MIN_BLOCKS")) min_blocks = std::atoi(env);
-    unsigned per_sm = 6;  // CTAs per SM in the grid: a multiple of every min_blocks variant's residency
+    if (const char* env = std::getenv("CAPSB_SCATTER_VARIANT")) variant = std::atoi(env);
+    unsigned per_sm = 6;  // CTAs per SM in the grid (three waves of the two resident CTAs)
     if (const char* env = std::getenv("CAPSB_SCATTER_CTAS_PER_SM")) per_sm = static_cast<unsigned>(std::atoi(env));
     max_blocks = static_cast<unsigned>(dev.sm_count) * (per_sm ? per_sm : 6);
     hist.alloc(static_cast<uint64_t>(kRadixSize) * max_blocks, stream);
@@ -318,31 +379,35 @@ struct RadixScratch {
   }
 };
 
-// Launches the scatter kernel variant selected by rs.min_blocks (register budget: 2 -> 128,
-// 3 -> 80, 4 -> 64 registers per thread; tuning knob CAPSB_SCATTER_MIN_BLOCKS).
-template <class KeyT, class ValT, class Src, int kMinBlocks>
+template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks>
 inline void launch_scatter_variant(cudaStream_t stream, RadixScratch& rs, const Chunking& ck, Src src, uint64_t n,
                                    unsigned shift, KeyT* keys_out, ValT* vals_out) {
-  constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT>);
+  constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT, kThreads, kItems>);
   static bool configured[64] = {};  // per template instantiation and device (the attribute is per context)
   const int slot = rs.device & 63;
   if (!configured[slot] || rs.device >= 64) {
-    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kMinBlocks>,
+    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
     configured[slot] = true;
   }
-  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src, kMinBlocks>), ck.blocks, kRsThreads, kSmem, stream, src, n,
-               ck.chunk, shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
+  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks>), ck.blocks, kThreads, kSmem, stream,
+               src, n, ck.chunk, shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
 }
 
 template <class KeyT, class ValT, class Src>
 inline void launch_scatter(cudaStream_t stream, RadixScratch& rs, const Chunking& ck, Src src, uint64_t n,
                            unsigned shift, KeyT* keys_out, ValT* vals_out) {
-  switch (rs.min_blocks) {
-    case 2: launch_scatter_variant<KeyT, ValT, Src, 2>(stream, rs, ck, src, n, shift, keys_out, vals_out); break;
-    case 4: launch_scatter_variant<KeyT, ValT, Src, 4>(stream, rs, ck, src, n, shift, keys_out, vals_out); break;
-    default: launch_scatter_variant<KeyT, ValT, Src, 3>(stream, rs, ck, src, n, shift, keys_out, vals_out); break;
+  // wide elements: one CTA per SM is all the shared memory allows
+  constexpr int kMin = (sizeof(KeyT) + sizeof(ValT)) * kRsTile <= 96 * 1024 ? 2 : 1;
+#ifdef CAPSB_RADIX_ALL_VARIANTS  // tools/radix_bench.cu
+  switch (rs.variant) {
+    case 0: launch_scatter_variant<KeyT, ValT, Src, 256, 16, kMin>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 2: launch_scatter_variant<KeyT, ValT, Src, 1024, 4, 1>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 3: launch_scatter_variant<KeyT, ValT, Src, 512, 8, 1>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    default: break;
   }
+#endif
+  launch_scatter_variant<KeyT, ValT, Src, 512, 8, kMin>(stream, rs, ck, src, n, shift, keys_out, vals_out);
 }
 
 // One stable counting pass on the 8-bit digit at `shift`.

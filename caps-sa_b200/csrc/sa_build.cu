@@ -91,22 +91,26 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     // ---- 4. prefix-doubling refinement of the tied groups --------------------------------
     {
       LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
-      refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, n, 0, n);
+      refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, n, 0, n);
     }
     key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
     clock.mark();  // 4
 
     // ---- 5. LCP of the tied neighbours: permuted-LCP recurrence on the deep positions ----
     {
-      // the tied pairs (i = SA[k], j = SA[k-1]) keyed by i; j and k travel as the sort's value
-      const uint64_t m = ties;
+      // the tied pairs (i = SA[k], j = SA[k-1]) the pair-chain step has not already settled,
+      // keyed by i; j and k travel as the sort's value
+      auto deep = [=] __device__(uint64_t k) -> uint64_t {
+        return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? 1u : 0u;
+      };
+      const uint64_t m = scan_total<uint64_t, OpSum>(eng, n, deep);
       DevBuf<IdxT> pos_a(m, st), pos_b(m, st);
       DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
       {
         IdxT* pa = pos_a.get();
         IdxPair<IdxT>* ta = tag_a.get();
-        scan_full<uint64_t, OpSum, false>(eng, n, tied, [=] __device__(uint64_t k, uint64_t slot) {
-          if (k > 0 && keys[k] == keys[k - 1]) {
+        scan_finish<uint64_t, OpSum, false>(eng, n, deep, [=] __device__(uint64_t k, uint64_t slot) {
+          if (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) {
             pa[slot] = d_sa[k];
             ta[slot] = IdxPair<IdxT>{d_sa[k - 1], static_cast<IdxT>(k)};
           }
@@ -118,8 +122,8 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
       const IdxT* pos_i = where ? pos_b.get() : pos_a.get();
       const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
       plcp_for_pairs<IdxT>(
-          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m,
-          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[tag[t].b] = lcp; });
+          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m, 0,
+          [=] __device__(uint64_t t, IdxT lcp, uint64_t, IdxT) { d_lcp[tag[t].b] = lcp; });
     }
     clock.mark();  // 5
   }

@@ -167,6 +167,28 @@ struct ShardedRanks {
     launch_map(eng.dev, eng.stream, rt.recv_total, [=] __device__(uint64_t j) { isa[rv[j].a - lo_] = rv[j].b; });
   }
 
+  // The pairs travel to the rank that owns text position hi: consecutive text positions land in
+  // unrelated buckets, so only there are the chains of chain_pairs_local contiguous.
+  void chain_pairs(IdxT* hi, const IdxT* lo, uint64_t m, uint64_t known, IdxPair<IdxT>* answer) {
+    cudaStream_t st = eng.stream;
+    const SliceMap mp = map;
+    Route<IdxT> rt = plan_route<IdxT>(eng, comm, m, [=] __device__(uint64_t t) -> unsigned { return mp.owner(hi[t]); });
+    const uint64_t got = rt.recv_total;
+    DevBuf<IdxPair<IdxT>> recv(got, st), ans(got, st);
+    route_forward<IdxPair<IdxT>>(
+        eng, comm, rt, [=] __device__(uint64_t t) -> IdxPair<IdxT> { return IdxPair<IdxT>{hi[t], lo[t]}; }, recv.get());
+    DevBuf<IdxT> r_hi(got, st), r_lo(got, st);
+    {
+      const IdxPair<IdxT>* rv = recv.get();
+      IdxT* h = r_hi.get();
+      IdxT* l = r_lo.get();
+      launch_map(eng.dev, st, got, [=] __device__(uint64_t j) { h[j] = rv[j].a, l[j] = rv[j].b; });
+    }
+    chain_pairs_local<IdxT>(eng, pt, r_hi.get(), r_lo.get(), got, known, ans.get());
+    route_backward<IdxPair<IdxT>>(eng, comm, rt, ans.get(),
+                                  [=] __device__(uint64_t t, IdxPair<IdxT> a) { answer[t] = a; });
+  }
+
   void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
     constexpr unsigned kField = IdxTraits<IdxT>::kField;
     cudaStream_t st = eng.stream;
@@ -417,16 +439,16 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     comm.all_gather_host(&ties, sizeof(ties), all.data(), st);
     for (uint64_t v : all) any_ties = any_ties || v > 0;
   }
+  out.lcp.alloc(bucket_count, st);
+  IdxT* d_lcp = out.lcp.get();
   if (any_ties) {
     ShardedRanks<IdxT> ranks(eng, comm, map, pt, key_mask_of(key_bits), sorted_samples, kSamplesPerRank, keys,
                              bucket_count, bucket_offset);
-    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, bucket_count, bucket_offset, n);
+    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, bucket_count, bucket_offset, n);
   }
   clock.mark("ties resolved");  // 5
 
   // ---- LCP ----------------------------------------------------------------------------------
-  out.lcp.alloc(bucket_count, st);
-  IdxT* d_lcp = out.lcp.get();
   {
     // the suffix that precedes this bucket is the last one of the nearest non-empty bucket below
     struct Edge {
@@ -448,15 +470,19 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     key_lcp<IdxT>(eng, keys, d_sa, d_lcp, bucket_count, n, log2_bits, has_prev, prev_key, prev_idx);
   }
   if (any_ties) {
-    // tied neighbours (always inside one bucket): the pair (i = SA[k], j = SA[k-1]) goes to the
-    // rank that owns text position i
-    DevBuf<IdxT> pair_i(ties, st), pair_j(ties, st), pair_k(ties, st);
+    // tied neighbours (always inside one bucket) that the pair-chain step has not settled: the
+    // pair (i = SA[k], j = SA[k-1]) goes to the rank that owns text position i
+    auto deep = [=] __device__(uint64_t k) -> uint64_t {
+      return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? 1u : 0u;
+    };
+    const uint64_t deep_count = scan_total<uint64_t, OpSum>(eng, bucket_count, deep);
+    DevBuf<IdxT> pair_i(deep_count, st), pair_j(deep_count, st), pair_k(deep_count, st);
     {
       IdxT* pi = pair_i.get();
       IdxT* pj = pair_j.get();
       IdxT* pk = pair_k.get();
-      scan_full<uint64_t, OpSum, false>(eng, bucket_count, tied, [=] __device__(uint64_t k, uint64_t slot) {
-        if (k > 0 && keys[k] == keys[k - 1]) {
+      scan_finish<uint64_t, OpSum, false>(eng, bucket_count, deep, [=] __device__(uint64_t k, uint64_t slot) {
+        if (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) {
           pi[slot] = d_sa[k];
           pj[slot] = d_sa[k - 1];
           pk[slot] = static_cast<IdxT>(k);
@@ -467,7 +493,8 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     const IdxT* pi = pair_i.get();
     const IdxT* pj = pair_j.get();
     const IdxT* pk = pair_k.get();
-    Route<IdxT> rt = plan_route<IdxT>(eng, comm, ties, [=] __device__(uint64_t t) -> unsigned { return mp.owner(pi[t]); });
+    Route<IdxT> rt =
+        plan_route<IdxT>(eng, comm, deep_count, [=] __device__(uint64_t t) -> unsigned { return mp.owner(pi[t]); });
     const uint64_t got = rt.recv_total;
     DevBuf<IdxPair<IdxT>> recv(got, st);
     route_forward<IdxPair<IdxT>>(
@@ -494,8 +521,8 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     {
       IdxT* ans = answers.get();
       plcp_for_pairs<IdxT>(
-          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, got,
-          [=] __device__(uint64_t t, IdxT lcp) { ans[tag[t].b] = lcp; });
+          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, got, 0,
+          [=] __device__(uint64_t t, IdxT lcp, uint64_t, IdxT) { ans[tag[t].b] = lcp; });
     }
     route_backward<IdxT>(eng, comm, rt, answers.get(),
                          [=] __device__(uint64_t t, IdxT lcp) { d_lcp[pk[t]] = lcp; });

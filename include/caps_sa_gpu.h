@@ -60,6 +60,7 @@ typedef struct caps_sa_gpu_stats {
   uint64_t comm_bytes;          /* bytes this rank moved to other ranks */
   uint64_t shard_offset;        /* this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count) */
   uint64_t shard_count;
+  uint64_t pairs_chained;       /* groups of two suffixes finished by the pair-chain step (order + LCP) */
 } caps_sa_gpu_stats;
 
 /* Number of CUDA devices visible to the library (0 if none / driver missing). */

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <vector>
 
+#define CAPSB_RADIX_ALL_VARIANTS 1
 #include "../caps-sa_b200/csrc/radix_sort.cuh"
 
 namespace capsb {
@@ -42,26 +43,45 @@ int main(int argc, char** argv) {
     rs.timer.enabled = true;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
-    for (int w = 0; w < 3; ++w)
-      radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
-                                     vb.get());
-    CAPSB_CUDA(cudaStreamSynchronize(st));
-    rs.timer.reset();
-    cudaEventRecord(e0, st);
-    for (int r = 0; r < reps; ++r)
-      radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
-                                     vb.get());
-    cudaEventRecord(e1, st);
-    CAPSB_CUDA(cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e0, e1);
-    uint32_t launches = 0;
-    const float scatter_ms = rs.timer.drain(&launches);
-    const double bytes = 24.0 * n;
-    printf("n=%llu min_blocks=%d grid_per_sm=%u: pass %.4f ms (%.1f GB/s incl. hist), scatter %.4f ms (%.1f GB/s, %.3f of 6650)\n",
-           (unsigned long long)n, rs.min_blocks, rs.max_blocks / dev.sm_count, ms / reps,
-           (bytes + 8.0 * n) / (ms / reps) / 1e6, scatter_ms / launches, bytes / (scatter_ms / launches) / 1e6,
-           bytes / (scatter_ms / launches) / 1e6 / 6650.0);
+    const char* names[] = {"256x16 mb2", "512x8 mb2", "1024x4 mb1", "512x8 mb1"};
+    for (int variant = 0; variant < 4; ++variant) {
+      if (argc > 4 && atoi(argv[4]) != variant) continue;
+      rs.variant = variant;
+      for (int w = 0; w < 3; ++w)
+        radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
+                                       vb.get());
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      rs.timer.reset();
+      cudaEventRecord(e0, st);
+      for (int r = 0; r < reps; ++r)
+        radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(),
+                                       vb.get());
+      cudaEventRecord(e1, st);
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      uint32_t launches = 0;
+      const float scatter_ms = rs.timer.drain(&launches);
+      const double bytes = 24.0 * n;
+      printf("n=%llu variant %d (%s) grid_per_sm=%u: pass %.4f ms (%.1f GB/s incl. hist), scatter %.4f ms (%.1f GB/s, %.3f of 6546)\n",
+             (unsigned long long)n, variant, names[variant], rs.max_blocks / dev.sm_count, ms / reps,
+             (bytes + 8.0 * n) / (ms / reps) / 1e6, scatter_ms / launches, bytes / (scatter_ms / launches) / 1e6,
+             bytes / (scatter_ms / launches) / 1e6 / 6546.0);
+    }
+    // correctness of the last variant run: output sorted by the digit, stable
+    {
+      std::vector<uint64_t> hk(1 << 20);
+      std::vector<uint32_t> hv(1 << 20);
+      const uint64_t take = n < hk.size() ? n : hk.size();
+      cudaMemcpy(hk.data(), kb.get(), take * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(hv.data(), vb.get(), take * 4, cudaMemcpyDeviceToHost);
+      bool ok = true;
+      for (uint64_t i = 1; i < take; ++i) {
+        const unsigned a = (hk[i - 1] >> shift) & 255, b = (hk[i] >> shift) & 255;
+        if (a > b || (a == b && hv[i - 1] >= hv[i])) ok = false;
+      }
+      printf("first %llu outputs sorted and stable: %s\n", (unsigned long long)take, ok ? "yes" : "NO");
+    }
   } catch (const std::exception& e) {
     fprintf(stderr, "error: %s\n", e.what());
     return 1;
