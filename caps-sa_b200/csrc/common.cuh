@@ -465,6 +465,63 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint64_t n, ui
   }
 }
 
+// Stream compaction: out(i, slot) for every i in the CTA's chunk with flag(i) != 0, slot = number
+// of flagged elements before i (partial[] holds the chunks' exclusive bases, as left by
+// scan_reduce + scan_spine over the same flags).  Flags are ballots, not values moved through
+// shared memory: per tile one ballot per row, an exclusive scan of the 64 (row, warp) counts by
+// one warp, and a popc — the general scan_apply_kernel costs ~3x as much on sparse selections.
+// other(i) is called for the elements that are not flagged.
+struct NoOther {
+  __device__ __forceinline__ void operator()(uint64_t) const {}
+};
+template <class T, class Flag, class Out, class Other>
+__global__ void __launch_bounds__(kScanThreads) select_apply_kernel(uint64_t n, uint64_t chunk, Flag flag, Out out,
+                                                                    Other other, const T* partial) {
+  static_assert(kScanItems * (kScanThreads / 32) == 64, "the (row, warp) counts are scanned by one warp, two each");
+  __shared__ unsigned counts[kScanItems * (kScanThreads / 32)];
+  __shared__ unsigned tile_total;
+  constexpr int kWarps = kScanThreads / 32;
+  const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
+  const uint64_t end = begin + chunk < n ? begin + chunk : n;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt = lanemask_lt();
+  T carry = partial[blockIdx.x];
+  for (uint64_t tile = begin; tile < end; tile += kScanTile) {
+    unsigned votes[kScanItems];
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const uint64_t i = tile + static_cast<unsigned>(k) * kScanThreads + threadIdx.x;
+      const bool f = i < end && flag(i) != 0;
+      votes[k] = __ballot_sync(0xffffffffu, f);
+      if (lane == 0) counts[k * kWarps + warp] = __popc(votes[k]);
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 64 counts in (row, warp) order = element order
+      const unsigned a = counts[2 * lane], b = counts[2 * lane + 1];
+      unsigned inc = a + b;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= static_cast<unsigned>(d)) inc += o;
+      }
+      counts[2 * lane] = inc - a - b;
+      counts[2 * lane + 1] = inc - b;
+      if (lane == 31) tile_total = inc;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+      const uint64_t i = tile + static_cast<unsigned>(k) * kScanThreads + threadIdx.x;
+      if (votes[k] >> lane & 1u)
+        out(i, static_cast<T>(carry + counts[k * kWarps + warp] + __popc(votes[k] & lt)));
+      else if (i < end)
+        other(i);
+    }
+    carry += tile_total;
+    __syncthreads();  // counts are rewritten by the next tile
+  }
+}
+
 // Scratch for scans (per-block partials); owned by the pipeline context.
 template <class T>
 struct ScanScratch {

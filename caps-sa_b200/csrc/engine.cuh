@@ -18,7 +18,7 @@ struct Stats {
   uint32_t bits_per_symbol = 0;
   uint32_t alphabet_size = 0;
   uint32_t refine_rounds = 0;
-  uint64_t tied_after_key_sort = 0;  // suffixes whose key equals their predecessor's
+  uint64_t tied_after_key_sort = 0;  // suffixes in key groups of two or more
   uint64_t refine_sorted = 0;        // suffix-rounds ordered by the radix sort (large groups)
   uint64_t refine_counted = 0;       // suffix-rounds ordered by counting inside small groups
   uint64_t deep_lcp_direct = 0;      // irreducible deep LCPs computed by comparison

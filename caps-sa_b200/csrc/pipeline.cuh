@@ -147,6 +147,16 @@ void scan_finish(Engine& eng, uint64_t n, In in, Out out) {
   CAPSB_LAUNCH((scan_apply_kernel<T, Op, Inclusive, In, Out>), ck.blocks, kScanThreads, 0, eng.stream, n,
                ck.chunk, in, out, sc.partial.get());
 }
+// Must directly follow scan_total<T, OpSum> over 0/1 flags: out(i, slot) for the flagged i only.
+// other(i) is called for the rest.
+template <class T, class Flag, class Out, class Other = NoOther>
+void select_finish(Engine& eng, uint64_t n, Flag flag, Out out, Other other = Other()) {
+  ScanScratch<T>& sc = eng.scan_scratch<T>();
+  if (n == 0) return;
+  const Chunking ck = make_chunking(n, kScanTile, sc.max_blocks);
+  CAPSB_LAUNCH((select_apply_kernel<T, Flag, Out, Other>), ck.blocks, kScanThreads, 0, eng.stream, n, ck.chunk, flag,
+               out, other, sc.partial.get());
+}
 template <class T, class Op, bool Inclusive, class In, class Out>
 void scan_full(Engine& eng, uint64_t n, In in, Out out) {
   device_scan<T, Op, Inclusive>(eng.dev, eng.stream, eng.scan_scratch<T>(), n, in, out);
@@ -202,7 +212,7 @@ struct LocalRanks {
   LocalRanks(Engine& e, uint64_t n_, const PackedText& pt_, const uint64_t* keys_, uint64_t key_mask_)
       : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_), isa(n_, e.stream) {}
 
-  bool any_active(uint64_t m) { return m > 0; }
+  uint64_t global_sum(uint64_t v) { return v; }  // over the ranks of the construction
 
   // every suffix starts with its SA position as rank: implicit (see above)
   void reset() { CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream)); }
@@ -261,6 +271,25 @@ struct LocalRanks {
 // order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
 // keys must be complete inside [0, count).
 // ---------------------------------------------------------------------------------------
+// LCP of two suffixes a, b (text positions) whose keys differ: clz(key_a ^ key_b) / bits, bounded
+// by the shorter suffix (zero padding can agree with real code-0 symbols past the end).
+template <class IdxT>
+__device__ __forceinline__ IdxT key_lcp_value(uint64_t key_a, uint64_t key_b, uint64_t a, uint64_t b, uint64_t n,
+                                              unsigned log2_bits) {
+  const uint64_t shorter = n - (a > b ? a : b);
+  const uint64_t l = static_cast<uint64_t>(__clzll(static_cast<long long>(key_a ^ key_b))) >> log2_bits;
+  return static_cast<IdxT>(l < shorter ? l : shorter);
+}
+
+// The local SA positions that were tied after the key sort (members of key groups of two or
+// more), in increasing order: what the stages after the refinement iterate over instead of
+// all n positions.
+template <class IdxT>
+struct TiedSet {
+  uint64_t m = 0;
+  DevBuf<IdxT> pos;
+};
+
 constexpr unsigned kSmallGroup = 32;  // groups up to this size are ordered by counting, not sorting
 
 // d_lcp value of a position whose LCP is still to be computed (an LCP is at most n - 1)
@@ -339,15 +368,11 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
     IdxT* h = hi.get();
     IdxT* l = lo.get();
     IdxT* sl = slot.get();
-    scan_finish<IdxT, OpSum, false>(eng, m, pair_first, [=] __device__(uint64_t t, IdxT j) {
-      const IdxT grp = g[t];
-      const bool first = static_cast<uint64_t>(p[t]) + pos_base == static_cast<uint64_t>(grp);
-      if (first && t + 1 < m && g[t + 1] == grp && (t + 2 >= m || g[t + 2] != grp)) {
-        const IdxT a = s[t], b = s[t + 1];
-        h[j] = a > b ? a : b;
-        l[j] = a > b ? b : a;
-        sl[j] = static_cast<IdxT>(t);
-      }
+    select_finish<IdxT>(eng, m, pair_first, [=] __device__(uint64_t t, IdxT j) {
+      const IdxT a = s[t], b = s[t + 1];
+      h[j] = a > b ? a : b;
+      l[j] = a > b ? b : a;
+      sl[j] = static_cast<IdxT>(t);
     });
   }
   ranks.chain_pairs(hi.get(), lo.get(), pairs, known, answer.get());
@@ -382,21 +407,16 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
     const bool pair = first + 1 < m && g[first + 1] == grp && (first + 2 >= m || g[first + 2] != grp);
     return pair ? IdxT(0) : IdxT(1);
   };
-  const uint64_t m_next = m - 2 * pairs;
+  const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, stays);  // = m - 2 * pairs
   DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
   if (m_next > 0) {
     IdxT* np = n_pos.get();
     IdxT* ns = n_idx.get();
     IdxT* ngp = n_group.get();
-    scan_full<IdxT, OpSum, false>(eng, m, stays, [=] __device__(uint64_t t, IdxT out) {
-      const IdxT grp = g[t];
-      const uint64_t first = t - (static_cast<uint64_t>(p[t]) + pos_base - static_cast<uint64_t>(grp));
-      const bool pair = first + 1 < m && g[first + 1] == grp && (first + 2 >= m || g[first + 2] != grp);
-      if (!pair) {
-        np[out] = p[t];
-        ns[out] = s[t];
-        ngp[out] = grp;
-      }
+    select_finish<IdxT>(eng, m, stays, [=] __device__(uint64_t t, IdxT out) {
+      np[out] = p[t];
+      ns[out] = s[t];
+      ngp[out] = g[t];
     });
   }
   act.pos = std::move(n_pos);
@@ -468,12 +488,10 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
         CompT* bc = bc_a.get();
         IdxT* bi = bi_a.get();
         IdxT* so = slot_of.get();
-        scan_finish<IdxT, OpSum, false>(eng, m, is_big, [=] __device__(uint64_t t, IdxT j) {
-          if (big[t]) {
-            bc[j] = c[t];
-            bi[j] = s[t];
-            so[j] = static_cast<IdxT>(t);
-          }
+        select_finish<IdxT>(eng, m, is_big, [=] __device__(uint64_t t, IdxT j) {
+          bc[j] = c[t];
+          bi[j] = s[t];
+          so[j] = static_cast<IdxT>(t);
         });
       }
       // LSD over the second field, then the group field
@@ -535,13 +553,10 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     IdxT* np = n_pos.get();
     IdxT* ns = n_idx.get();
     IdxT* ngp = n_group.get();
-    scan_finish<IdxT, OpSum, false>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
-      const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
-      if (!single) {
-        np[slot] = p[t];
-        ns[slot] = sorted_idx[t];
-        ngp[slot] = ng[t];
-      }
+    select_finish<IdxT>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
+      np[slot] = p[t];
+      ns[slot] = sorted_idx[t];
+      ngp[slot] = ng[t];
     });
   }
   act.pos = std::move(n_pos);
@@ -565,15 +580,18 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
 // ---------------------------------------------------------------------------------------
 template <class IdxT, class Ranks>
 void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
-                        IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n) {
+                        IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n, TiedSet<IdxT>& tied) {
   using Comp = typename IdxTraits<IdxT>::Comp;
   constexpr unsigned kField = IdxTraits<IdxT>::kField;
   using Wide = unsigned __int128;
   cudaStream_t st = eng.stream;
 
-  ranks.reset();
+  const unsigned log2_bits = pt.log2_bits;
 
-  // the suffixes still to be ordered: members of key groups with at least two suffixes
+  // The suffixes still to be ordered: members of key groups with at least two suffixes.  The same
+  // pass writes every LCP that the keys alone decide (neighbours with different keys) and marks
+  // the rest unset; entries next to a tied group are provisional (their bound depends on which
+  // member ends up at the group's edge) and are rewritten by fix_group_edge_lcp afterwards.
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
     const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
     return tied ? IdxT(1) : IdxT(0);
@@ -583,19 +601,26 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
   act.pos.alloc(act.m, st);
   act.idx.alloc(act.m, st);
   act.group.alloc(act.m, st);
+  tied.m = act.m;
+  tied.pos.alloc(act.m, st);
   {
     IdxT* p = act.pos.get();
+    IdxT* p0 = tied.pos.get();
     IdxT* s = act.idx.get();
     IdxT* g = act.group.get();
-    scan_finish<IdxT, OpSum, false>(eng, count, in_group, [=] __device__(uint64_t k, IdxT slot) {
-      const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
-      if (tied) {
-        p[slot] = static_cast<IdxT>(k);
-        s[slot] = d_sa[k];
-        // LCP with a tied predecessor: unknown until the pair-chain step or the deep-LCP stage
-        if (k > 0 && keys[k] == keys[k - 1]) d_lcp[k] = kLcpUnset<IdxT>;
-      }
-    });
+    select_finish<IdxT>(
+        eng, count, in_group,
+        [=] __device__(uint64_t k, IdxT slot) {
+          p[slot] = p0[slot] = static_cast<IdxT>(k);
+          s[slot] = d_sa[k];
+          if (k > 0)
+            d_lcp[k] = keys[k] == keys[k - 1]
+                           ? kLcpUnset<IdxT>  // until the pair-chain step or the deep-LCP stage
+                           : key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+        },
+        [=] __device__(uint64_t k) {
+          if (k > 0) d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+        });
     // group head (global SA position) of every active suffix: running maximum of the heads
     scan_full<IdxT, OpMax, true>(
         eng, act.m,
@@ -606,8 +631,9 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
         [=] __device__(uint64_t t, IdxT head) { g[t] = head; });
   }
 
+  uint64_t total_active = ranks.global_sum(act.m);
+  if (total_active > 0) ranks.reset();
   const unsigned rank_bits = round_up8(bit_length(n - 1));
-  const unsigned log2_bits = pt.log2_bits;
   uint64_t h = key_bits >> log2_bits;  // the key sort ordered the suffixes by that many symbols
   const bool trace = trace_enabled();
   std::chrono::steady_clock::time_point round_start;
@@ -617,15 +643,24 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
                  (unsigned long long)act.m, (unsigned long long)h);
   }
   bool first_round = true;
-  while (ranks.any_active(act.m)) {
-    // groups of two are finished directly (order and LCP); the rest goes through a doubling round
-    resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h);
-    if (trace) {
-      CAPSB_CUDA(cudaStreamSynchronize(st));
-      std::fprintf(stderr, "[capsb] pairs finished so far: %llu, active now %llu\n",
-                   (unsigned long long)eng.stats.pairs_chained, (unsigned long long)act.m);
+  bool try_pairs = true;
+  for (unsigned iter = 0; total_active > 0; ++iter) {
+    // groups of two are finished directly (order and LCP); the rest goes through a doubling round.
+    // The step is a few passes over the list, so it stops once it no longer thins the list out.
+    if (try_pairs) {
+      if (trace) round_start = std::chrono::steady_clock::now();
+      const uint64_t before = total_active;
+      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h);
+      total_active = ranks.global_sum(act.m);
+      try_pairs = iter < 2 || (before - total_active) * 16 >= before;
+      if (trace) {
+        CAPSB_CUDA(cudaStreamSynchronize(st));
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
+        std::fprintf(stderr, "[capsb] pair chains: active %llu -> %llu  %.3f ms\n", (unsigned long long)before,
+                     (unsigned long long)total_active, ms);
+      }
+      if (total_active == 0) break;
     }
-    if (!ranks.any_active(act.m)) break;
     eng.stats.refine_rounds++;
     if (trace) round_start = std::chrono::steady_clock::now();
     const uint64_t m = act.m;
@@ -663,7 +698,57 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     }
     if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
     h <<= 1;
+    total_active = ranks.global_sum(act.m);
   }
+
+  // key-derived LCPs at the two edges of every key group, now that the members there are final
+  {
+    const IdxT* p0 = tied.pos.get();
+    launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
+      const uint64_t k = p0[t];
+      if (k > 0 && keys[k] != keys[k - 1])
+        d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+      if (k + 1 < count && keys[k + 1] != keys[k])
+        d_lcp[k + 1] = key_lcp_value<IdxT>(keys[k], keys[k + 1], d_sa[k], d_sa[k + 1], n, log2_bits);
+    });
+  }
+}
+
+// LCP of local position 0: against (prev_key, prev_idx), the last suffix of the bucket before
+// this one (its key differs), or 0 at the very start of the suffix array.
+template <class IdxT>
+void first_position_lcp(Engine& eng, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t n,
+                        unsigned log2_bits, bool has_prev, uint64_t prev_key, uint64_t prev_idx) {
+  if (count == 0) return;
+  launch_map(eng.dev, eng.stream, 1, [=] __device__(uint64_t) {
+    d_lcp[0] = has_prev ? key_lcp_value<IdxT>(prev_key, keys[0], prev_idx, d_sa[0], n, log2_bits) : IdxT(0);
+  });
+}
+
+// The tied neighbours whose LCP is still unset after the refinement (everything the pair-chain
+// step did not settle): pair_i = SA[k], pair_j = SA[k-1], pair_k = k.  Returns their number.
+template <class IdxT>
+uint64_t collect_deep_pairs(Engine& eng, const TiedSet<IdxT>& tied, const uint64_t* keys, const IdxT* d_sa,
+                            const IdxT* d_lcp, DevBuf<IdxT>& pair_i, DevBuf<IdxT>& pair_j, DevBuf<IdxT>& pair_k) {
+  const IdxT* p0 = tied.pos.get();
+  auto deep = [=] __device__(uint64_t t) -> IdxT {
+    const uint64_t k = p0[t];
+    return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? IdxT(1) : IdxT(0);
+  };
+  const uint64_t m = scan_total<IdxT, OpSum>(eng, tied.m, deep);
+  pair_i.alloc(m, eng.stream);
+  pair_j.alloc(m, eng.stream);
+  pair_k.alloc(m, eng.stream);
+  IdxT* pi = pair_i.get();
+  IdxT* pj = pair_j.get();
+  IdxT* pk = pair_k.get();
+  select_finish<IdxT>(eng, tied.m, deep, [=] __device__(uint64_t t, IdxT slot) {
+    const uint64_t k = p0[t];
+    pi[slot] = d_sa[k];
+    pj[slot] = d_sa[k - 1];
+    pk[slot] = static_cast<IdxT>(k);
+  });
+  return m;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -769,11 +854,15 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ p
       const bool chained =
           t > 0 && static_cast<uint64_t>(pos_i[t - 1]) + 1 == i && i > 0 && j > 0 && pt.symbol(i - 1) == pt.symbol(j - 1);
       ch[t] = chained ? IdxT(0) : static_cast<IdxT>(t);
+      // statistics: one atomic per warp, not per pair (every lane of a warp adds to one address)
+      const unsigned active = __activemask();
+      const unsigned heads = __ballot_sync(active, !chained);
+      if (heads != 0 && (threadIdx.x & 31u) == static_cast<unsigned>(__ffs(static_cast<int>(heads)) - 1))
+        atomicAdd(cnt + 0, static_cast<unsigned long long>(__popc(heads)));
       if (!chained) {
         uint64_t l = 0;
         const bool done = pt.common_prefix(i, j, known, 16, &l);
         pl[t] = static_cast<IdxT>(l);
-        atomicAdd(cnt + 0, 1ull);
         if (!done) td[atomicAdd(cnt + 1, 1ull)] = static_cast<IdxT>(t);
       }
     });

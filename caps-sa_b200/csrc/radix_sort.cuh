@@ -309,6 +309,20 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src
   for (int i = tid; i < (kThreads / 32) * kRsMatchSlots * (kRadixSize + 1); i += kThreads)
     (&sm.match[0][0][0])[i] = 0;
 
+#ifdef CAPSB_RADIX_EXPERIMENT_TILE_ORDER
+  // tools/radix_bench.cu only (results are garbage): tiles dealt round-robin to the CTAs and written
+  // where a tile-ordered (onesweep-style) pass would put them, assuming 16 elements per digit and tile
+  __shared__ uint64_t digit_base[kRadixSize];
+  __syncthreads();
+  if (tid < kRadixSize) digit_base[tid] = sm.run_base[tid] - hist[static_cast<uint64_t>(tid) * gridDim.x + blockIdx.x];
+  const uint64_t full_tiles = n / kTile;
+  for (uint64_t ti = blockIdx.x; ti < full_tiles; ti += gridDim.x) {
+    __syncthreads();
+    if (tid < kRadixSize) sm.run_base[tid] = digit_base[tid] + ti * (kTile / kRadixSize);
+    scatter_tile<true, KeyT, ValT, Src, kThreads, kItems>(sm, src, ti * kTile, kTile, shift, keys_out, vals_out);
+  }
+  (void)chunk;
+#else
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
   uint64_t tile = begin;
@@ -317,6 +331,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src
   if (tile < end)
     scatter_tile<false, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, static_cast<unsigned>(end - tile), shift,
                                                           keys_out, vals_out);
+#endif
 }
 
 // Host driver ---------------------------------------------------------------------------

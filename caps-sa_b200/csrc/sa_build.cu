@@ -76,57 +76,43 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   sort_suffix_slice<IdxT>(eng, pt, 0, n, key_bits, key_buf.get(), d_sa);
   const uint64_t* keys = key_buf.get();
   clock.mark();  // 2
-
-  // ---- 3. count the suffixes whose key ties with their predecessor --------------------------
-  auto tied = [=] __device__(uint64_t k) -> uint64_t { return (k > 0 && keys[k] == keys[k - 1]) ? 1u : 0u; };
-  const uint64_t ties = scan_total<uint64_t, OpSum>(eng, n, tied);
-  eng.stats.tied_after_key_sort = ties;
   clock.mark();  // 3
 
-  if (ties == 0) {
-    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
-    clock.mark();  // 4
-    clock.mark();  // 5
-  } else {
-    // ---- 4. prefix-doubling refinement of the tied groups --------------------------------
-    {
-      LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
-      refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, n, 0, n);
-    }
-    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
-    clock.mark();  // 4
-
-    // ---- 5. LCP of the tied neighbours: permuted-LCP recurrence on the deep positions ----
-    {
-      // the tied pairs (i = SA[k], j = SA[k-1]) the pair-chain step has not already settled,
-      // keyed by i; j and k travel as the sort's value
-      auto deep = [=] __device__(uint64_t k) -> uint64_t {
-        return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? 1u : 0u;
-      };
-      const uint64_t m = scan_total<uint64_t, OpSum>(eng, n, deep);
-      DevBuf<IdxT> pos_a(m, st), pos_b(m, st);
-      DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
-      {
-        IdxT* pa = pos_a.get();
-        IdxPair<IdxT>* ta = tag_a.get();
-        scan_finish<uint64_t, OpSum, false>(eng, n, deep, [=] __device__(uint64_t k, uint64_t slot) {
-          if (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) {
-            pa[slot] = d_sa[k];
-            ta[slot] = IdxPair<IdxT>{d_sa[k - 1], static_cast<IdxT>(k)};
-          }
-        });
-      }
-      const unsigned pos_bits = round_up8(bit_length(n - 1));
-      const int where = radix_sort_pairs<IdxT, IdxPair<IdxT>>(st, eng.radix, pos_a.get(), tag_a.get(), pos_b.get(),
-                                                             tag_b.get(), m, 0, pos_bits);
-      const IdxT* pos_i = where ? pos_b.get() : pos_a.get();
-      const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
-      plcp_for_pairs<IdxT>(
-          eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m, 0,
-          [=] __device__(uint64_t t, IdxT lcp, uint64_t, IdxT) { d_lcp[tag[t].b] = lcp; });
-    }
-    clock.mark();  // 5
+  // ---- 3. ties: prefix-doubling refinement + pair chains; LCPs the keys decide ---------------
+  TiedSet<IdxT> tied;
+  {
+    LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
+    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, n, 0, n, tied);
   }
+  first_position_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
+  eng.stats.tied_after_key_sort = tied.m;
+  clock.mark();  // 4
+
+  // ---- 4. LCP of the tied neighbours still open: permuted-LCP recurrence ---------------------
+  if (tied.m > 0) {
+    // the pairs (i = SA[k], j = SA[k-1]) keyed by i; j and k travel as the sort's value
+    DevBuf<IdxT> pos_a, pair_j, pair_k;
+    const uint64_t m = collect_deep_pairs<IdxT>(eng, tied, keys, d_sa, d_lcp, pos_a, pair_j, pair_k);
+    DevBuf<IdxT> pos_b(m, st);
+    DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
+    {
+      const IdxT* pj = pair_j.get();
+      const IdxT* pk = pair_k.get();
+      IdxPair<IdxT>* ta = tag_a.get();
+      launch_map(eng.dev, st, m, [=] __device__(uint64_t t) { ta[t] = IdxPair<IdxT>{pj[t], pk[t]}; });
+    }
+    pair_j.release();
+    pair_k.release();
+    const unsigned pos_bits = round_up8(bit_length(n - 1));
+    const int where = radix_sort_pairs<IdxT, IdxPair<IdxT>>(st, eng.radix, pos_a.get(), tag_a.get(), pos_b.get(),
+                                                           tag_b.get(), m, 0, pos_bits);
+    const IdxT* pos_i = where ? pos_b.get() : pos_a.get();
+    const IdxPair<IdxT>* tag = where ? tag_b.get() : tag_a.get();
+    plcp_for_pairs<IdxT>(
+        eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m, 0,
+        [=] __device__(uint64_t t, IdxT lcp, uint64_t, IdxT) { d_lcp[tag[t].b] = lcp; });
+  }
+  clock.mark();  // 5
 
   clock.mark();  // 6
   CAPSB_CUDA(cudaStreamSynchronize(st));

@@ -146,12 +146,12 @@ struct ShardedRanks {
     CAPSB_CUDA(cudaMemsetAsync(isa_local.get(), 0xFF, isa_local.size() * sizeof(IdxT), eng.stream));
   }
 
-  bool any_active(uint64_t m) {
+  uint64_t global_sum(uint64_t v) {
     std::vector<uint64_t> all(static_cast<size_t>(comm.world));
-    comm.all_gather_host(&m, sizeof(m), all.data(), eng.stream);
-    for (uint64_t v : all)
-      if (v) return true;
-    return false;
+    comm.all_gather_host(&v, sizeof(v), all.data(), eng.stream);
+    uint64_t sum = 0;
+    for (uint64_t x : all) sum += x;
+    return sum;
   }
 
   // isa[idx[t]] = head[t] on the rank that owns text position idx[t], for t in [0, m)
@@ -429,28 +429,22 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   IdxT* d_sa = out.sa.get();
   clock.mark("merged");  // 4
 
-  // ---- ties ---------------------------------------------------------------------------------
-  auto tied = [=] __device__(uint64_t k) -> uint64_t { return (k > 0 && keys[k] == keys[k - 1]) ? 1u : 0u; };
-  const uint64_t ties = scan_total<uint64_t, OpSum>(eng, bucket_count, tied);
-  eng.stats.tied_after_key_sort = ties;
-  bool any_ties = false;
-  {
-    std::vector<uint64_t> all(world);
-    comm.all_gather_host(&ties, sizeof(ties), all.data(), st);
-    for (uint64_t v : all) any_ties = any_ties || v > 0;
-  }
+  // ---- ties (collective: every rank runs the same number of rounds) ---------------------------
   out.lcp.alloc(bucket_count, st);
   IdxT* d_lcp = out.lcp.get();
-  if (any_ties) {
+  TiedSet<IdxT> tied;
+  {
     ShardedRanks<IdxT> ranks(eng, comm, map, pt, key_mask_of(key_bits), sorted_samples, kSamplesPerRank, keys,
                              bucket_count, bucket_offset);
-    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, bucket_count, bucket_offset, n);
+    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, bucket_count, bucket_offset, n, tied);
   }
+  eng.stats.tied_after_key_sort = tied.m;
   clock.mark("ties resolved");  // 5
 
   // ---- LCP ----------------------------------------------------------------------------------
   {
     // the suffix that precedes this bucket is the last one of the nearest non-empty bucket below
+    // (the reference's partition-boundary patch, src/Suffix_Array.cpp:431-447)
     struct Edge {
       uint64_t count, last_key, last_idx;
     } mine{bucket_count, 0, 0};
@@ -467,28 +461,13 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     uint64_t prev_key = 0, prev_idx = 0;
     for (unsigned q = 0; q < rank; ++q)
       if (edges[q].count) has_prev = true, prev_key = edges[q].last_key, prev_idx = edges[q].last_idx;
-    key_lcp<IdxT>(eng, keys, d_sa, d_lcp, bucket_count, n, log2_bits, has_prev, prev_key, prev_idx);
+    first_position_lcp<IdxT>(eng, keys, d_sa, d_lcp, bucket_count, n, log2_bits, has_prev, prev_key, prev_idx);
   }
-  if (any_ties) {
+  {
     // tied neighbours (always inside one bucket) that the pair-chain step has not settled: the
     // pair (i = SA[k], j = SA[k-1]) goes to the rank that owns text position i
-    auto deep = [=] __device__(uint64_t k) -> uint64_t {
-      return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? 1u : 0u;
-    };
-    const uint64_t deep_count = scan_total<uint64_t, OpSum>(eng, bucket_count, deep);
-    DevBuf<IdxT> pair_i(deep_count, st), pair_j(deep_count, st), pair_k(deep_count, st);
-    {
-      IdxT* pi = pair_i.get();
-      IdxT* pj = pair_j.get();
-      IdxT* pk = pair_k.get();
-      scan_finish<uint64_t, OpSum, false>(eng, bucket_count, deep, [=] __device__(uint64_t k, uint64_t slot) {
-        if (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) {
-          pi[slot] = d_sa[k];
-          pj[slot] = d_sa[k - 1];
-          pk[slot] = static_cast<IdxT>(k);
-        }
-      });
-    }
+    DevBuf<IdxT> pair_i, pair_j, pair_k;
+    const uint64_t deep_count = collect_deep_pairs<IdxT>(eng, tied, keys, d_sa, d_lcp, pair_i, pair_j, pair_k);
     const SliceMap mp = map;
     const IdxT* pi = pair_i.get();
     const IdxT* pj = pair_j.get();

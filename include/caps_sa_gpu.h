@@ -41,7 +41,7 @@ typedef struct caps_sa_gpu_stats {
   uint32_t bits_per_symbol;     /* 1, 2, 4 or 8: width of the packed codes */
   uint32_t alphabet_size;
   uint32_t refine_rounds;       /* prefix-doubling rounds run on the tied suffixes */
-  uint64_t tied_after_key_sort; /* suffixes whose 64-bit key equals their predecessor's */
+  uint64_t tied_after_key_sort; /* suffixes whose sort key is shared with another suffix */
   uint64_t deep_lcp_direct;     /* irreducible deep LCPs computed by direct comparison */
   uint64_t deep_lcp_long;       /* ... that needed the block-wide comparison */
   uint64_t kernel_launches;     /* launches of this library's kernels */

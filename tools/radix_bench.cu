@@ -36,8 +36,8 @@ int main(int argc, char** argv) {
     CAPSB_CUDA(cudaStreamCreate(&st));
     RadixScratch rs;
     rs.init(dev, st);
-    DevBuf<uint64_t> ka(n, st), kb(n, st);
-    DevBuf<uint32_t> va(n, st), vb(n, st);
+    DevBuf<uint64_t> ka(n, st), kb(n + (8u << 20), st);  // slack: the TILE_ORDER experiment overshoots
+    DevBuf<uint32_t> va(n, st), vb(n + (8u << 20), st);
     fill_random<<<dev.sm_count * 8, 256, 0, st>>>(ka.get(), va.get(), n);
     CAPSB_CUDA(cudaStreamSynchronize(st));
     rs.timer.enabled = true;
