@@ -89,11 +89,12 @@ inline void trace_point(Engine& eng, const char* what) {
   static const auto t0 = std::chrono::steady_clock::now();
   cudaStreamSynchronize(eng.stream);
   const uint64_t reserved = eng.arena.reserved(), used = eng.arena.used();
-  size_t free_b = 0, total_b = 0;
-  cudaMemGetInfo(&free_b, &total_b);
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-  std::fprintf(stderr, "[capsb dev%d] %10.3f ms  %-22s arena reserved %.2f GB used %.2f GB, device free %.2f GB\n",
-               eng.dev.device, ms, what, reserved / 1e9, used / 1e9, free_b / 1e9);
+  static thread_local double last_ms = 0;
+  // (no cudaMemGetInfo here: it takes milliseconds and lands in whichever interval follows)
+  std::fprintf(stderr, "[capsb dev%d] %10.3f ms (+%8.3f)  %-40s arena reserved %.2f GB used %.2f GB\n", eng.dev.device, ms,
+               ms - last_ms, what, reserved / 1e9, used / 1e9);
+  last_ms = ms;
 }
 
 // Stage timer: records an event now; elapsed times are read at the end.
@@ -425,6 +426,58 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
   act.m = m_next;
 }
 
+// Groups of kSmallGroup < size <= kMidGroup suffixes (the bulk of a repeat family's ties) are
+// sorted by one CTA each, in shared memory (bitonic network on (comp, suffix)): two passes over
+// their elements in HBM instead of the 7-9 radix passes the global sort would spend on them.
+constexpr unsigned kMidGroup = 4096;
+constexpr int kGroupSortThreads = 256;
+
+template <class CompT, class IdxT>
+__global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const IdxT* __restrict__ group_first,
+                                                                       const IdxT* __restrict__ group_size,
+                                                                       const unsigned long long* __restrict__ group_count,
+                                                                       const CompT* __restrict__ comp_in,
+                                                                       const IdxT* __restrict__ idx_in,
+                                                                       CompT* __restrict__ comp_out,
+                                                                       IdxT* __restrict__ idx_out) {
+  extern __shared__ __align__(16) unsigned char group_sort_smem[];
+  CompT* k = reinterpret_cast<CompT*>(group_sort_smem);
+  IdxT* v = reinterpret_cast<IdxT*>(group_sort_smem + sizeof(CompT) * kMidGroup);
+  const unsigned long long groups = *group_count;
+  for (unsigned long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+    const uint64_t first = group_first[grp];
+    const unsigned size = static_cast<unsigned>(group_size[grp]);
+    unsigned padded = 64;
+    while (padded < size) padded <<= 1;
+    for (unsigned e = threadIdx.x; e < padded; e += kGroupSortThreads) {
+      k[e] = e < size ? comp_in[first + e] : ~CompT(0);  // padding sorts last
+      v[e] = e < size ? idx_in[first + e] : IdxT(0);
+    }
+    __syncthreads();
+    for (unsigned span = 2; span <= padded; span <<= 1) {
+      for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
+        for (unsigned pr = threadIdx.x; pr < (padded >> 1); pr += kGroupSortThreads) {
+          const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
+          const unsigned j = i | stride;
+          const bool up = (i & span) == 0;
+          const CompT a = k[i], b = k[j];
+          if ((a > b) == up && a != b) {
+            k[i] = b, k[j] = a;
+            const IdxT va = v[i];
+            v[i] = v[j], v[j] = va;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (unsigned e = threadIdx.x; e < size; e += kGroupSortThreads) {
+      comp_out[first + e] = k[e];
+      idx_out[first + e] = v[e];
+    }
+    __syncthreads();  // the staging area is refilled by the next group
+  }
+}
+
 // One refinement round on the active list.  comp_a[t] = group field (the group head plus one
 // for suffixes that reach depth h inside the text) above a `second` field whose bits
 // [second_lo, second_hi) order the members of a group; CompT's group field starts at bit
@@ -440,26 +493,51 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   DevBuf<IdxT> idx_b(m, st), head_slot(m, st);
 
   // Order every group by the second field.  Groups of at most kSmallGroup suffixes — after the
-  // first rounds nearly all of them: pairs left by long exact repeats — are ranked by counting
-  // inside the group (one pass, no sort); the rest is radix-sorted by (group, second).
+  // first rounds nearly all of them — are ranked by counting inside the group (one pass, no
+  // sort); groups of up to kMidGroup are sorted by one CTA each in shared memory; only the rest
+  // (poly-A runs, tandem arrays, periodic texts) is radix-sorted by (group, second).
   CompT* sorted_c = comp_b.get();
   IdxT* sorted_i = idx_b.get();
+  trace_point(eng, "  round: comps built");
   DevBuf<uint8_t> big_flag(m, st);
+  const uint64_t mid_capacity = m / (kSmallGroup + 1) + 1;
+  DevBuf<IdxT> mid_first(mid_capacity, st), mid_size(mid_capacity, st);
+  DevBuf<unsigned long long> mid_count(1, st);
+  CAPSB_CUDA(cudaMemsetAsync(mid_count.get(), 0, sizeof(unsigned long long), st));
   {
     const CompT* c = comp_a.get();
     const IdxT* s = act.idx.get();
     const IdxT* g = act.group.get();
     const IdxT* p = act.pos.get();
     uint8_t* big = big_flag.get();
+    IdxT* mf = mid_first.get();
+    IdxT* ms = mid_size.get();
+    unsigned long long* mc = mid_count.get();
     launch_map(dev, st, m, [=] __device__(uint64_t t) {
       const IdxT grp = g[t];
       // the members of a group are consecutive in the list, in SA order
       const uint64_t first = t - (static_cast<uint64_t>(p[t]) - (static_cast<uint64_t>(grp) - pos_base));
-      if (first + kSmallGroup < m && g[first + kSmallGroup] == grp) {
+      if (first + kMidGroup < m && g[first + kMidGroup] == grp) {
         big[t] = 1;
         return;
       }
       big[t] = 0;
+      if (first + kSmallGroup < m && g[first + kSmallGroup] == grp) {
+        if (t == first) {  // the group's first member announces it: last index with the same head
+          uint64_t lo = first + kSmallGroup, hi = first + kMidGroup < m ? first + kMidGroup : m;  // g[lo] == grp, g[hi] != grp
+          while (hi - lo > 1) {
+            const uint64_t mid = (lo + hi) >> 1;
+            if (g[mid] == grp)
+              lo = mid;
+            else
+              hi = mid;
+          }
+          const unsigned long long slot = atomicAdd(mc, 1ull);
+          mf[slot] = static_cast<IdxT>(first);
+          ms[slot] = static_cast<IdxT>(hi - first);
+        }
+        return;
+      }
       const CompT mine = c[t];
       unsigned rank = 0;
       for (uint64_t u = first; u < m && u < first + kSmallGroup && g[u] == grp; ++u) {
@@ -469,7 +547,20 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
       sorted_c[first + rank] = mine;
       sorted_i[first + rank] = s[t];
     });
+    trace_point(eng, "  round: classified + small groups counted");
+    constexpr size_t kSortSmem = (sizeof(CompT) + sizeof(IdxT)) * kMidGroup;
+    static bool configured[64] = {};
+    if (!configured[dev.device & 63]) {
+      CAPSB_CUDA(cudaFuncSetAttribute(group_sort_kernel<CompT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(kSortSmem)));
+      configured[dev.device & 63] = true;
+    }
+    const uint64_t want = mid_capacity < static_cast<uint64_t>(dev.sm_count) * 8 ? mid_capacity
+                                                                                   : static_cast<uint64_t>(dev.sm_count) * 8;
+    CAPSB_LAUNCH((group_sort_kernel<CompT, IdxT>), static_cast<unsigned>(want), kGroupSortThreads, kSortSmem, st,
+                 mid_first.get(), mid_size.get(), mid_count.get(), c, s, sorted_c, sorted_i);
   }
+  trace_point(eng, "  round: mid groups sorted");
   {
     const uint8_t* big = big_flag.get();
     auto is_big = [=] __device__(uint64_t t) -> IdxT { return big[t]; };
@@ -521,6 +612,7 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   }
   const CompT* sorted_comp = sorted_c;
   const IdxT* sorted_idx = sorted_i;
+  trace_point(eng, "  round: large groups sorted");
 
   IdxT* hs = head_slot.get();
   scan_full<IdxT, OpMax, true>(
@@ -539,7 +631,9 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
       ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
     });
   }
+  trace_point(eng, "  round: heads + sa written");
   ranks.publish(sorted_idx, new_group.get(), m);
+  trace_point(eng, "  round: ranks published");
 
   auto still_tied = [=] __device__(uint64_t t) -> IdxT {
     const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
