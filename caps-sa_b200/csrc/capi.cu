@@ -149,6 +149,31 @@ int check_context(uint64_t max_context, uint64_t n) {
   return CAPS_SA_GPU_OK;
 }
 
+// Text staging of the sharded construction from a host buffer: every rank uploads only its own
+// 1/world of the text over its own PCIe link and the ranks all-gather the pieces over NVLink
+// (in place), instead of every rank pulling the whole text through PCIe.
+struct StagedText {
+  capsb::DevBuf<uint8_t> buf;  // piece * world bytes >= n
+  float ms_h2d = 0;
+};
+StagedText stage_text_sharded(Engine& eng, capsb::Comm& comm, const char* text, uint64_t n) {
+  cudaStream_t st = eng.stream;
+  const uint64_t world = static_cast<uint64_t>(comm.world), rank = static_cast<uint64_t>(comm.rank);
+  const uint64_t piece = (capsb::ceil_div(n, world) + 15) / 16 * 16;
+  StagedText out;
+  out.buf.alloc(piece * world, st);
+  const uint64_t lo = rank * piece < n ? rank * piece : n;
+  const uint64_t hi = (rank + 1) * piece < n ? (rank + 1) * piece : n;
+  EventPair h2d;
+  CAPSB_CUDA(cudaEventRecord(h2d.a, st));
+  if (hi > lo) CAPSB_CUDA(cudaMemcpyAsync(out.buf.get() + lo, text + lo, hi - lo, cudaMemcpyHostToDevice, st));
+  CAPSB_CUDA(cudaEventRecord(h2d.b, st));
+  if (world > 1) comm.all_gather_device(out.buf.get() + rank * piece, out.buf.get(), piece, st);
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+  out.ms_h2d = h2d.ms();
+  return out;
+}
+
 // One process, one host thread per rank, peer copies between the ranks (ThreadComm).
 template <class IdxT>
 int construct_multi(const int* devices, int num_ranks, const char* text, uint64_t n, IdxT* sa_out, IdxT* lcp_out,
@@ -176,13 +201,9 @@ int construct_multi(const int* devices, int num_ranks, const char* text, uint64_
             cudaStream_t st = eng.stream;
             capsb::ShardResult<IdxT> shard;
             {
-              capsb::DevBuf<uint8_t> d_text(n, st);
-              EventPair h2d;
-              CAPSB_CUDA(cudaEventRecord(h2d.a, st));
-              CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
-              CAPSB_CUDA(cudaEventRecord(h2d.b, st));
-              capsb::build_sa_lcp_sharded<IdxT>(eng, comm, d_text.get(), n, shard);
-              eng.stats.ms_h2d = h2d.ms();
+              StagedText staged = stage_text_sharded(eng, comm, text, n);
+              capsb::build_sa_lcp_sharded<IdxT>(eng, comm, staged.buf.get(), n, shard);
+              eng.stats.ms_h2d = staged.ms_h2d;
             }
             EventPair d2h;
             CAPSB_CUDA(cudaEventRecord(d2h.a, st));
@@ -240,13 +261,9 @@ int construct_sharded_host(caps_sa_gpu_engine* engine, const char* text, uint64_
     capsb::ShardResult<IdxT>& shard = shard_of<IdxT>(eng);
     float ms_h2d = 0;
     {
-      capsb::DevBuf<uint8_t> d_text(n, st);
-      EventPair h2d;
-      CAPSB_CUDA(cudaEventRecord(h2d.a, st));
-      CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
-      CAPSB_CUDA(cudaEventRecord(h2d.b, st));
-      capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, d_text.get(), n, shard);
-      ms_h2d = h2d.ms();
+      StagedText staged = stage_text_sharded(eng, *eng.comm, text, n);
+      capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, staged.buf.get(), n, shard);
+      ms_h2d = staged.ms_h2d;
     }
     EventPair d2h;
     CAPSB_CUDA(cudaEventRecord(d2h.a, st));

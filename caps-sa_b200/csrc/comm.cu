@@ -99,7 +99,7 @@ void ThreadComm::all_gather_device(const void* send, void* recv, size_t bytes, c
   for (int s = 0; s < world; ++s) {
     const ThreadGroup::Slot& src = group_->slot(s);
     char* to = static_cast<char*>(recv) + static_cast<size_t>(s) * bytes;
-    if (!bytes) continue;
+    if (!bytes || to == src.ptr) continue;  // in place: the own piece is already there
     if (src.device == device_)
       CAPSB_CUDA(cudaMemcpyAsync(to, src.ptr, bytes, cudaMemcpyDeviceToDevice, st));
     else
@@ -118,7 +118,7 @@ void SelfComm::all_to_all_v(const void* send, const uint64_t* send_counts, void*
 }
 void SelfComm::all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t) { std::memcpy(out, in, bytes); }
 void SelfComm::all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) {
-  if (bytes) CAPSB_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
+  if (bytes && send != recv) CAPSB_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
 }
 
 // ---- NCCL, resolved at run time ---------------------------------------------------------

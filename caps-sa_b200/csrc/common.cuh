@@ -388,8 +388,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_reduce_kernel(uint64_t n, u
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
   T acc = Op::template identity<T>();
-  for (uint64_t i = begin + threadIdx.x; i < end; i += kScanThreads)
-    acc = Op::template apply<T>(acc, in(i));
+  uint64_t i = begin + threadIdx.x;
+  for (; i + 3 * kScanThreads < end; i += 4 * kScanThreads) {  // four independent elements in flight
+    const T a = in(i), b = in(i + kScanThreads), c = in(i + 2 * kScanThreads), d = in(i + 3 * kScanThreads);
+    acc = Op::template apply<T>(Op::template apply<T>(acc, Op::template apply<T>(a, b)), Op::template apply<T>(c, d));
+  }
+  for (; i < end; i += kScanThreads) acc = Op::template apply<T>(acc, in(i));
   T inc, total;
   block_scan<T, Op>(acc, &inc, &total, smem);
   if (threadIdx.x == 0) partial[blockIdx.x] = total;
@@ -491,7 +495,8 @@ __global__ void __launch_bounds__(kScanThreads) select_apply_kernel(uint64_t n, 
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
       const uint64_t i = tile + static_cast<unsigned>(k) * kScanThreads + threadIdx.x;
-      const bool f = i < end && flag(i) != 0;
+      // flag() of a clamped index rather than a branch around it: the rows' loads stay independent
+      const bool f = (flag(i < end ? i : end - 1) != 0) & (i < end);
       votes[k] = __ballot_sync(0xffffffffu, f);
       if (lane == 0) counts[k * kWarps + warp] = __popc(votes[k]);
     }

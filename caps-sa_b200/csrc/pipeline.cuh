@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "engine.cuh"
 
@@ -167,9 +168,9 @@ void scan_full(Engine& eng, uint64_t n, In in, Out out) {
 // Key sort of the suffixes [base, base + count): on return keys_out / sa_out hold them in key
 // order (keys masked to key_bits).  keys_out and sa_out are caller-owned, `count` entries.
 // ---------------------------------------------------------------------------------------
-template <class IdxT>
-void sort_suffix_slice(Engine& eng, const PackedText& pt, uint64_t base, uint64_t count, unsigned key_bits,
-                       uint64_t* keys_out, IdxT* sa_out) {
+template <class IdxT, class FirstSrc>
+void sort_suffixes_by_key(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
+                          IdxT* sa_out) {
   if (count == 0) return;
   cudaStream_t st = eng.stream;
   const unsigned passes = key_bits / 8;
@@ -181,14 +182,33 @@ void sort_suffix_slice(Engine& eng, const PackedText& pt, uint64_t base, uint64_
   IdxT* val_buf[2];
   key_buf[last] = keys_out, val_buf[last] = sa_out;
   key_buf[last ^ 1u] = key_tmp.get(), val_buf[last ^ 1u] = val_tmp.get();
-  radix_pass<uint64_t, IdxT>(st, eng.radix, TextSource<IdxT>{pt, key_mask_of(key_bits), base}, count, 64 - key_bits,
-                             key_buf[0], val_buf[0]);
+  radix_pass<uint64_t, IdxT>(st, eng.radix, first, count, 64 - key_bits, key_buf[0], val_buf[0]);
   for (unsigned q = 1; q < passes; ++q) {
     const unsigned in = (q - 1) & 1u, out = q & 1u;
     radix_pass<uint64_t, IdxT>(st, eng.radix, ArraySource<uint64_t, IdxT>{key_buf[in], val_buf[in]}, count,
                                64 - key_bits + 8 * q, key_buf[out], val_buf[out]);
   }
 }
+
+// The suffixes [base, base + count) of the text.
+template <class IdxT>
+void sort_suffix_slice(Engine& eng, const PackedText& pt, uint64_t base, uint64_t count, unsigned key_bits,
+                       uint64_t* keys_out, IdxT* sa_out) {
+  sort_suffixes_by_key<IdxT>(eng, TextSource<IdxT>{pt, key_mask_of(key_bits), base}, count, key_bits, keys_out, sa_out);
+}
+
+// First radix pass over a list of suffixes: key = window at suffix idx[i].  The lists this is
+// used on are runs of increasing text positions, so the window reads stream through the
+// packed text.
+template <class IdxT>
+struct SuffixListSource {
+  PackedText pt;
+  uint64_t mask;
+  const IdxT* idx;
+  __device__ __forceinline__ uint64_t key(uint64_t i) const { return pt.window(idx[i]) & mask; }
+  __device__ __forceinline__ IdxT val(uint64_t i) const { return idx[i]; }
+  static constexpr uint64_t bytes_read_per_item() { return 2 * sizeof(IdxT) + 1; }
+};
 
 // ---------------------------------------------------------------------------------------
 // Rank storage of the single-GPU path: isa[text position] = first SA position of the
@@ -209,14 +229,17 @@ struct LocalRanks {
   PackedText pt;
   const uint64_t* keys;  // sorted (masked) keys of all n suffixes
   uint64_t key_mask;
-  DevBuf<IdxT> isa;
+  DevBuf<IdxT> isa;  // allocated when the refinement first needs ranks (reset)
   LocalRanks(Engine& e, uint64_t n_, const PackedText& pt_, const uint64_t* keys_, uint64_t key_mask_)
-      : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_), isa(n_, e.stream) {}
+      : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_) {}
 
   uint64_t global_sum(uint64_t v) { return v; }  // over the ranks of the construction
 
   // every suffix starts with its SA position as rank: implicit (see above)
-  void reset() { CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream)); }
+  void reset() {
+    if (!isa) isa.alloc(n, eng.stream);
+    CAPSB_CUDA(cudaMemsetAsync(isa.get(), 0xFF, n * sizeof(IdxT), eng.stream));
+  }
 
   // isa[idx[t]] = head[t] for t in [0, m)
   void publish(const IdxT* idx, const IdxT* head, uint64_t m) {
@@ -229,10 +252,10 @@ struct LocalRanks {
     chain_pairs_local<IdxT>(eng, pt, hi, lo, m, known, answer);
   }
 
-  // comp[t] = (group[t] + inside) << field | second, where second is the rank of suffix
-  // idx[t] + h, or n - 1 - idx[t] beyond the end (shorter suffix first = larger position first)
-  void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
-    constexpr unsigned kField = IdxTraits<IdxT>::kField;
+  // second[t] = rank of suffix idx[t] + h, or n - 1 - idx[t] when that is beyond the end of the
+  // text (shorter suffix first = larger position first; the caller ranks those below every
+  // suffix that reaches depth h)
+  void second_ranks(const IdxT* idx, uint64_t m, uint64_t h, IdxT* second_out) {
     const IdxT* d_isa = isa.get();
     const uint64_t n_ = n;
     const PackedText text = pt;
@@ -241,9 +264,8 @@ struct LocalRanks {
     launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) {
       const uint64_t i = idx[t];
       const uint64_t ih = i + h;
-      const bool inside = ih < n_;
       uint64_t second = n_ - 1 - i;
-      if (inside) {
+      if (ih < n_) {
         const IdxT r = d_isa[ih];
         if (r != kUnset) {
           second = r;
@@ -260,8 +282,7 @@ struct LocalRanks {
           second = lo;
         }
       }
-      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
-                static_cast<Comp>(second);
+      second_out[t] = static_cast<IdxT>(second);
     });
   }
 };
@@ -346,11 +367,11 @@ void chain_pairs_local(Engine& eng, const PackedText& pt, IdxT* hi, const IdxT* 
 }
 
 // Finishes every group of two in the active list: final order into d_sa, their LCP into d_lcp,
-// ranks published, and the pairs leave the list.  Collective in the sharded path (the pairs
+// ranks published (once the refinement keeps ranks), and the pairs leave the list.  Collective in the sharded path (the pairs
 // travel to the rank that owns text position hi, where the chains are contiguous).
 template <class IdxT, class Ranks>
 void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa, IdxT* d_lcp, uint64_t pos_base,
-                   uint64_t known) {
+                   uint64_t known, bool publish) {
   cudaStream_t st = eng.stream;
   const uint64_t m = act.m;
   const IdxT* p = act.pos.get();
@@ -358,8 +379,9 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
   const IdxT* g = act.group.get();
   auto pair_first = [=] __device__(uint64_t t) -> IdxT {
     const IdxT grp = g[t];
+    const IdxT g1 = g[t + 1 < m ? t + 1 : t], g2 = g[t + 2 < m ? t + 2 : t];  // unconditional loads
     const bool first = static_cast<uint64_t>(p[t]) + pos_base == static_cast<uint64_t>(grp);
-    return (first && t + 1 < m && g[t + 1] == grp && (t + 2 >= m || g[t + 2] != grp)) ? IdxT(1) : IdxT(0);
+    return (first & (t + 1 < m) & (g1 == grp) & ((t + 2 >= m) | (g2 != grp))) ? IdxT(1) : IdxT(0);
   };
   const uint64_t pairs = scan_total<IdxT, OpSum>(eng, m, pair_first);
   eng.stats.pairs_chained += pairs;
@@ -399,7 +421,7 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
       pi[2 * j + 1] = large, ph[2 * j + 1] = static_cast<IdxT>(pos_base + k + 1);
     });
   }
-  ranks.publish(pub_idx.get(), pub_head.get(), 2 * pairs);
+  if (publish) ranks.publish(pub_idx.get(), pub_head.get(), 2 * pairs);
 
   if (pairs == 0) return;
   auto stays = [=] __device__(uint64_t t) -> IdxT {
@@ -450,26 +472,44 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const Idx
     unsigned padded = 64;
     while (padded < size) padded <<= 1;
     for (unsigned e = threadIdx.x; e < padded; e += kGroupSortThreads) {
-      k[e] = e < size ? comp_in[first + e] : ~CompT(0);  // padding sorts last
-      v[e] = e < size ? idx_in[first + e] : IdxT(0);
+      // padding sorts last: largest key and a suffix index no suffix has
+      k[e] = e < size ? comp_in[first + e] : ~CompT(0);
+      v[e] = e < size ? idx_in[first + e] : ~IdxT(0);
     }
     __syncthreads();
+    // Every warp owns a contiguous eighth of the padded group: compare-exchange steps whose
+    // stride stays inside it (all but the last few of each merge) need only a warp barrier.
+    const unsigned warp_pairs = padded >> 4;  // pairs per warp's range (padded / 8 elements)
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    auto exchange = [&](unsigned pr, unsigned span, unsigned stride) {
+      const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
+      const unsigned j = i | stride;
+      const bool up = (i & span) == 0;
+      const CompT a = k[i], b = k[j];
+      const IdxT va = v[i], vb = v[j];
+      const bool greater = a > b || (a == b && va > vb);  // (comp, suffix) pairs are distinct
+      if (greater == up) {
+        k[i] = b, k[j] = a;
+        v[i] = vb, v[j] = va;
+      }
+    };
+    bool block_wide = false;  // was the previous step synchronised across the block?
     for (unsigned span = 2; span <= padded; span <<= 1) {
       for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
-        for (unsigned pr = threadIdx.x; pr < (padded >> 1); pr += kGroupSortThreads) {
-          const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
-          const unsigned j = i | stride;
-          const bool up = (i & span) == 0;
-          const CompT a = k[i], b = k[j];
-          if ((a > b) == up && a != b) {
-            k[i] = b, k[j] = a;
-            const IdxT va = v[i];
-            v[i] = v[j], v[j] = va;
-          }
+        if (stride >= warp_pairs) {  // crosses the warps' ranges
+          __syncthreads();
+          for (unsigned pr = threadIdx.x; pr < (padded >> 1); pr += kGroupSortThreads) exchange(pr, span, stride);
+          __syncthreads();
+          block_wide = true;
+        } else {
+          (void)block_wide;
+          for (unsigned pr = lane; pr < warp_pairs; pr += 32) exchange(warp * warp_pairs + pr, span, stride);
+          __syncwarp();
+          block_wide = false;
         }
-        __syncthreads();
       }
     }
+    __syncthreads();
     for (unsigned e = threadIdx.x; e < size; e += kGroupSortThreads) {
       comp_out[first + e] = k[e];
       idx_out[first + e] = v[e];
@@ -478,14 +518,17 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const Idx
   }
 }
 
-// One refinement round on the active list.  comp_a[t] = group field (the group head plus one
-// for suffixes that reach depth h inside the text) above a `second` field whose bits
-// [second_lo, second_hi) order the members of a group; CompT's group field starts at bit
-// kGroupShift.  Orders every group, writes the new order to d_sa, publishes the new group heads
-// and drops the suffixes that are now alone in their group.
-template <class IdxT, class CompT, unsigned kGroupShift, class Ranks>
+// One refinement round on the active list.  comp_a[t] orders the members of a group: the low
+// second_bits bits are the second key (text beyond the current depth, or a rank); with
+// kGroupInComp the group head (plus one for suffixes that reach the current depth inside the
+// text) sits above it, at bit 32 (64-bit comps) or 64 (128-bit comps), otherwise the comps
+// carry no group and only the large-group sort prepends it.  Orders every group, writes the new
+// order to d_sa, publishes the new group heads (when the refinement keeps ranks) and drops the
+// suffixes that are now alone in their group.
+template <class IdxT, class CompT, bool kGroupInComp, class Ranks>
 void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_base, DevBuf<CompT> comp_a,
-                  unsigned second_lo, unsigned second_hi, unsigned rank_bits, Ranks& ranks) {
+                  unsigned second_bits, unsigned rank_bits, Ranks* publish_to) {
+  using Wide = unsigned __int128;
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
   const uint64_t m = act.m;
@@ -571,41 +614,50 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
       std::fprintf(stderr, "[capsb]   round: %llu suffixes in small groups (counted), %llu in large groups (sorted)\n",
                    (unsigned long long)(m - big_count), (unsigned long long)big_count);
     if (big_count > 0) {
-      DevBuf<CompT> bc_a(big_count, st), bc_b(big_count, st);
+      // sort key of the large groups: the group head above the comp (already there when kGroupInComp)
+      using BigKey = std::conditional_t<kGroupInComp, CompT, Wide>;
+      constexpr unsigned kGroupShift = kGroupInComp ? sizeof(CompT) * 4 : 64;
+      DevBuf<BigKey> bc_a(big_count, st), bc_b(big_count, st);
       DevBuf<IdxT> bi_a(big_count, st), bi_b(big_count, st), slot_of(big_count, st);
       {
         const CompT* c = comp_a.get();
         const IdxT* s = act.idx.get();
-        CompT* bc = bc_a.get();
+        const IdxT* g = act.group.get();
+        BigKey* bc = bc_a.get();
         IdxT* bi = bi_a.get();
         IdxT* so = slot_of.get();
         select_finish<IdxT>(eng, m, is_big, [=] __device__(uint64_t t, IdxT j) {
-          bc[j] = c[t];
+          bc[j] = kGroupInComp ? static_cast<BigKey>(c[t])
+                               : static_cast<BigKey>((static_cast<Wide>(static_cast<uint64_t>(g[t])) << 64) |
+                                                     static_cast<Wide>(c[t]));
           bi[j] = s[t];
           so[j] = static_cast<IdxT>(t);
         });
       }
       // LSD over the second field, then the group field
-      CompT* kin = bc_a.get();
+      BigKey* kin = bc_a.get();
       IdxT* vin = bi_a.get();
-      CompT* kout = bc_b.get();
+      BigKey* kout = bc_b.get();
       IdxT* vout = bi_b.get();
       auto passes = [&](unsigned lo, unsigned hi) {
         for (unsigned shift = lo; shift < hi; shift += 8) {
-          radix_pass<CompT, IdxT>(st, eng.radix, ArraySource<CompT, IdxT>{kin, vin}, big_count, shift, kout, vout);
+          radix_pass<BigKey, IdxT>(st, eng.radix, ArraySource<BigKey, IdxT>{kin, vin}, big_count, shift, kout, vout);
           std::swap(kin, kout);
           std::swap(vin, vout);
         }
       };
-      passes(second_lo, second_hi);
-      passes(kGroupShift, kGroupShift + rank_bits);
+      passes(0, second_bits);
+      {  // the group field (with the in-range bit added into it when kGroupInComp)
+        const unsigned top = kGroupShift + rank_bits + 8;
+        passes(kGroupShift, top < sizeof(BigKey) * 8 ? top : static_cast<unsigned>(sizeof(BigKey) * 8));
+      }
       // the sorted sub-list keeps the groups in list order, so its j-th element belongs in the
       // j-th slot that a large group occupies
       const IdxT* so = slot_of.get();
-      const CompT* sc = kin;
+      const BigKey* sc = kin;
       const IdxT* si = vin;
       launch_map(dev, st, big_count, [=] __device__(uint64_t j) {
-        sorted_c[so[j]] = sc[j];
+        sorted_c[so[j]] = static_cast<CompT>(sc[j]);
         sorted_i[so[j]] = si[j];
       });
     }
@@ -615,10 +667,14 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   trace_point(eng, "  round: large groups sorted");
 
   IdxT* hs = head_slot.get();
+  const IdxT* old_group = act.group.get();
   scan_full<IdxT, OpMax, true>(
       eng, m,
       [=] __device__(uint64_t t) -> IdxT {
-        return (t > 0 && sorted_comp[t] != sorted_comp[t - 1]) ? static_cast<IdxT>(t) : IdxT(0);
+        // a new group starts where the comp changes or the old group does (comps without a group
+        // field can agree across a boundary)
+        return (t > 0 && (sorted_comp[t] != sorted_comp[t - 1] || old_group[t] != old_group[t - 1])) ? static_cast<IdxT>(t)
+                                                                                                  : IdxT(0);
       },
       [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
 
@@ -632,11 +688,14 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     });
   }
   trace_point(eng, "  round: heads + sa written");
-  ranks.publish(sorted_idx, new_group.get(), m);
-  trace_point(eng, "  round: ranks published");
+  if (publish_to) {
+    publish_to->publish(sorted_idx, new_group.get(), m);
+    trace_point(eng, "  round: ranks published");
+  }
 
   auto still_tied = [=] __device__(uint64_t t) -> IdxT {
-    const bool single = hs[t] == t && (t + 1 == m || hs[t + 1] == t + 1);
+    const IdxT h0 = hs[t], h1 = hs[t + 1 < m ? t + 1 : t];  // unconditional loads
+    const bool single = (h0 == t) & ((t + 1 == m) | (h1 == t + 1));
     return single ? IdxT(0) : IdxT(1);
   };
   const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
@@ -686,9 +745,11 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
   // pass writes every LCP that the keys alone decide (neighbours with different keys) and marks
   // the rest unset; entries next to a tied group are provisional (their bound depends on which
   // member ends up at the group's edge) and are rewritten by fix_group_edge_lcp afterwards.
+  // (all loads unconditional, on clamped indices: a short-circuit would chain their latencies)
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
-    const bool tied = (k > 0 && keys[k] == keys[k - 1]) || (k + 1 < count && keys[k + 1] == keys[k]);
-    return tied ? IdxT(1) : IdxT(0);
+    const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
+    const uint64_t a = keys[kp], b = keys[k], c = keys[kn];
+    return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
   };
   ActiveList<IdxT> act;
   act.m = scan_total<IdxT, OpSum>(eng, count, in_group);
@@ -705,15 +766,20 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     select_finish<IdxT>(
         eng, count, in_group,
         [=] __device__(uint64_t k, IdxT slot) {
+          const uint64_t kp = k > 0 ? k - 1 : 0;
+          const uint64_t ka = keys[kp], kb = keys[k];
+          const IdxT sa_prev = d_sa[kp], sa_here = d_sa[k];
           p[slot] = p0[slot] = static_cast<IdxT>(k);
-          s[slot] = d_sa[k];
+          s[slot] = sa_here;
           if (k > 0)
-            d_lcp[k] = keys[k] == keys[k - 1]
-                           ? kLcpUnset<IdxT>  // until the pair-chain step or the deep-LCP stage
-                           : key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+            d_lcp[k] = ka == kb ? kLcpUnset<IdxT>  // until the pair-chain step or the deep-LCP stage
+                                : key_lcp_value<IdxT>(ka, kb, sa_prev, sa_here, n, log2_bits);
         },
         [=] __device__(uint64_t k) {
-          if (k > 0) d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+          const uint64_t kp = k > 0 ? k - 1 : 0;
+          const uint64_t ka = keys[kp], kb = keys[k];
+          const IdxT sa_prev = d_sa[kp], sa_here = d_sa[k];
+          if (k > 0) d_lcp[k] = key_lcp_value<IdxT>(ka, kb, sa_prev, sa_here, n, log2_bits);
         });
     // group head (global SA position) of every active suffix: running maximum of the heads
     scan_full<IdxT, OpMax, true>(
@@ -726,75 +792,110 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
   }
 
   uint64_t total_active = ranks.global_sum(act.m);
-  if (total_active > 0) ranks.reset();
   const unsigned rank_bits = round_up8(bit_length(n - 1));
   uint64_t h = key_bits >> log2_bits;  // the key sort ordered the suffixes by that many symbols
   const bool trace = trace_enabled();
   std::chrono::steady_clock::time_point round_start;
   if (trace) {
-    CAPSB_CUDA(cudaStreamSynchronize(st));
     std::fprintf(stderr, "[capsb] refine: count=%llu active=%llu h0=%llu\n", (unsigned long long)count,
                  (unsigned long long)act.m, (unsigned long long)h);
+    trace_point(eng, "tied set built, key LCPs written");
   }
-  bool first_round = true;
+  auto lap = [&](const char* what, uint64_t before) {
+    if (!trace) return;
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
+    std::fprintf(stderr, "[capsb] %s: h=%llu active %llu -> %llu  %.3f ms\n", what, (unsigned long long)h,
+                 (unsigned long long)before, (unsigned long long)total_active, ms);
+  };
+
+  // Two kinds of round.  TEXT rounds order every group by the text that follows the current
+  // depth (the next 63 bits of the packed text, read directly): they need no rank array, so in
+  // the sharded path they involve no exchange at all, and they clear the shallow ties — repeat
+  // families, accidental key collisions — which are nearly all of them.  RANK rounds are prefix
+  // doubling proper (second key = rank of suffix i + h): the depth doubles, which is what deep
+  // ties (tandem arrays, periodic texts) need.  The switch happens when a text round stops
+  // thinning the list; at that point every suffix that was ever tied publishes its group head
+  // once (never-tied suffixes keep implicit ranks, see LocalRanks / ShardedRanks).
+  const uint64_t text_step = 63u >> log2_bits;  // symbols a text round advances
+  bool rank_phase = false;
   bool try_pairs = true;
   for (unsigned iter = 0; total_active > 0; ++iter) {
-    // groups of two are finished directly (order and LCP); the rest goes through a doubling round.
-    // The step is a few passes over the list, so it stops once it no longer thins the list out.
+    // groups of two are finished directly (order and LCP).  The step is a few passes over the
+    // list, so it stops once it no longer thins the list out.
     if (try_pairs) {
       if (trace) round_start = std::chrono::steady_clock::now();
       const uint64_t before = total_active;
-      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h);
+      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h, rank_phase);
       total_active = ranks.global_sum(act.m);
       try_pairs = iter < 2 || (before - total_active) * 16 >= before;
-      if (trace) {
-        CAPSB_CUDA(cudaStreamSynchronize(st));
-        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
-        std::fprintf(stderr, "[capsb] pair chains: active %llu -> %llu  %.3f ms\n", (unsigned long long)before,
-                     (unsigned long long)total_active, ms);
-      }
+      lap("pair chains", before);
       if (total_active == 0) break;
     }
     eng.stats.refine_rounds++;
     if (trace) round_start = std::chrono::steady_clock::now();
     const uint64_t m = act.m;
-    if (first_round) {
-      // second field = key of suffix i + h (top key_bits of the low 64 bits); beyond the end of
-      // the text: n - 1 - i in the same bits, under a group field one lower (shorter suffix first)
-      const IdxT* idx = act.idx.get();
-      const IdxT* group = act.group.get();
+    const uint64_t before = total_active;
+    const IdxT* idx = act.idx.get();
+    if (!rank_phase) {
+      // comp = 1 . (next 63 bits of text) for suffixes that reach depth h, else 0 . (n - 1 - i):
+      // the shorter suffix first, i.e. the larger position first
       const PackedText text = pt;
-      const uint64_t mask = key_mask_of(key_bits);
-      const unsigned low = 64 - key_bits;
       const uint64_t depth = h;
-      DevBuf<Wide> comp(m, st);
-      Wide* c = comp.get();
+      DevBuf<uint64_t> comp(m, st);
+      uint64_t* c = comp.get();
       launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
         const uint64_t i = idx[t];
         const uint64_t ih = i + depth;
-        const bool inside = ih < n;
-        const uint64_t second = inside ? (text.window(ih) & mask) : ((n - 1 - i) << low);
-        c[t] = (static_cast<Wide>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << 64) |
-               static_cast<Wide>(second);
+        c[t] = ih < n ? (1ull << 63) | (text.window(ih) >> 1) : (n - 1 - i);
       });
-      refine_round<IdxT, Wide, 64>(eng, act, d_sa, pos_base, std::move(comp), low, 64, rank_bits, ranks);
-      first_round = false;
+      refine_round<IdxT, uint64_t, false, Ranks>(eng, act, d_sa, pos_base, std::move(comp), 64, rank_bits, nullptr);
+      h += text_step;
+      total_active = ranks.global_sum(act.m);
+      lap("text round", before);
+      // a text round that leaves more than 3/4 of the list tied: the rest is deep, switch to doubling
+      if (total_active > 0 && total_active * 4 > before * 3) {
+        if (trace) round_start = std::chrono::steady_clock::now();
+        rank_phase = true;
+        ranks.reset();
+        {  // every ever-tied suffix publishes its SA position; the still-tied ones then their group head
+          const IdxT* p0 = tied.pos.get();
+          DevBuf<IdxT> all_idx(tied.m, st), all_pos(tied.m, st);
+          IdxT* ai = all_idx.get();
+          IdxT* ap = all_pos.get();
+          launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
+            ai[t] = d_sa[p0[t]];
+            ap[t] = static_cast<IdxT>(pos_base + p0[t]);
+          });
+          ranks.publish(ai, ap, tied.m);
+        }
+        ranks.publish(act.idx.get(), act.group.get(), act.m);
+        lap("ranks published (switch to doubling)", total_active);
+      }
     } else {
+      DevBuf<IdxT> second(m, st);
+      ranks.second_ranks(idx, m, h, second.get());
       DevBuf<Comp> comp(m, st);
-      ranks.make_comp(act.idx.get(), act.group.get(), m, h, comp.get());
-      refine_round<IdxT, Comp, kField>(eng, act, d_sa, pos_base, std::move(comp), 0, rank_bits, rank_bits, ranks);
+      {
+        const IdxT* sec = second.get();
+        const IdxT* group = act.group.get();
+        Comp* c = comp.get();
+        launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
+          const bool inside = static_cast<uint64_t>(idx[t]) + h < n;
+          c[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
+                 static_cast<Comp>(sec[t]);
+        });
+      }
+      second.release();
+      refine_round<IdxT, Comp, true, Ranks>(eng, act, d_sa, pos_base, std::move(comp), rank_bits, rank_bits, &ranks);
+      if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
+      h <<= 1;
+      total_active = ranks.global_sum(act.m);
+      lap("rank round", before);
     }
-    if (trace) {
-      CAPSB_CUDA(cudaStreamSynchronize(st));
-      const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
-      std::fprintf(stderr, "[capsb] refine round %u: h=%llu active=%llu -> %llu  %.3f ms\n", eng.stats.refine_rounds,
-                   (unsigned long long)h, (unsigned long long)m, (unsigned long long)act.m, ms);
-    }
-    if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
-    h <<= 1;
-    total_active = ranks.global_sum(act.m);
   }
 
+  trace_point(eng, "ties resolved");
   // key-derived LCPs at the two edges of every key group, now that the members there are final
   {
     const IdxT* p0 = tied.pos.get();
@@ -827,7 +928,9 @@ uint64_t collect_deep_pairs(Engine& eng, const TiedSet<IdxT>& tied, const uint64
   const IdxT* p0 = tied.pos.get();
   auto deep = [=] __device__(uint64_t t) -> IdxT {
     const uint64_t k = p0[t];
-    return (k > 0 && keys[k] == keys[k - 1] && d_lcp[k] == kLcpUnset<IdxT>) ? IdxT(1) : IdxT(0);
+    const uint64_t a = keys[k > 0 ? k - 1 : 0], b = keys[k];  // unconditional loads (see in_group)
+    const IdxT l = d_lcp[k];
+    return ((k > 0) & (a == b) & (l == kLcpUnset<IdxT>)) ? IdxT(1) : IdxT(0);
   };
   const uint64_t m = scan_total<IdxT, OpSum>(eng, tied.m, deep);
   pair_i.alloc(m, eng.stream);

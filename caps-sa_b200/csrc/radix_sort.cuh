@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -24,7 +25,7 @@ constexpr int kRadixBits = 8;
 constexpr int kRadixSize = 1 << kRadixBits;
 constexpr int kRsThreads = 256;         // histogram kernel
 constexpr int kRsWarps = kRsThreads / 32;
-constexpr int kRsTile = 4096;           // scatter tile (every layout: threads x items = 4096); chunks are multiples
+constexpr int kRsTile = 8192;           // chunks are multiples of this; every scatter layout's tile (threads x items) divides it
 
 template <class KeyT>
 __device__ __forceinline__ unsigned radix_digit(KeyT key, unsigned shift) {
@@ -39,7 +40,15 @@ struct ArraySource {
   __device__ __forceinline__ KeyT key(uint64_t i) const { return keys[i]; }
   __device__ __forceinline__ ValT val(uint64_t i) const { return vals[i]; }
   static constexpr uint64_t bytes_read_per_item() { return sizeof(KeyT) + sizeof(ValT); }
+  // keys are plain memory: the scatter kernel may fetch the next tile's keys asynchronously
+  static constexpr bool kDirectKeys = true;
+  __device__ __forceinline__ const KeyT* key_ptr(uint64_t i) const { return keys + i; }
 };
+
+template <class Src, class = void>
+struct HasDirectKeys : std::false_type {};
+template <class Src>
+struct HasDirectKeys<Src, std::enable_if_t<Src::kDirectKeys>> : std::true_type {};
 
 // Kernels -------------------------------------------------------------------------------
 template <class KeyT, class Src>
@@ -108,9 +117,11 @@ struct ScatterCfg {
   static constexpr bool kSeparate = (sizeof(KeyT) + sizeof(ValT)) * kTile <= 56 * 1024;
 };
 
-template <class KeyT, class ValT, int kThreads, int kItems>
+template <class KeyT, class ValT, int kThreads, int kItems, bool kPrefetch = false>
 struct ScatterSmem {
   using Cfg = ScatterCfg<KeyT, ValT, kThreads, kItems>;
+  // next tile's keys, fetched with cp.async while this tile is written out: [item][thread]
+  alignas(16) KeyT prefetch[kPrefetch ? Cfg::kTile : 1];
   static constexpr size_t kStageBytes =
       Cfg::kSeparate ? (sizeof(KeyT) + sizeof(ValT)) * Cfg::kTile
                      : (sizeof(KeyT) > sizeof(ValT) ? sizeof(KeyT) : sizeof(ValT)) * Cfg::kTile;
@@ -146,10 +157,13 @@ __device__ __forceinline__ uint64_t digit_scan(uint64_t v, uint64_t* smem /*[8]*
 }
 
 // One tile of the scatter pass.  kFull = the tile has all kTile elements (no bounds checks).
-template <bool kFull, class KeyT, class ValT, class Src, int kThreads, int kItems>
-__device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, kItems>& sm, const Src& src,
+// kPrefetched: this tile's keys are already on their way to sm.prefetch (cp.async);
+// next_tile/next_valid (kPrefetch only): the tile whose keys to fetch while this one is written out.
+template <bool kFull, bool kPrefetch, class KeyT, class ValT, class Src, int kThreads, int kItems>
+__device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, kItems, kPrefetch>& sm, const Src& src,
                                              uint64_t tile, unsigned valid, unsigned shift,
-                                             KeyT* __restrict__ keys_out, ValT* __restrict__ vals_out) {
+                                             KeyT* __restrict__ keys_out, ValT* __restrict__ vals_out,
+                                             bool prefetched, uint64_t next_tile, unsigned next_valid) {
   using Cfg = ScatterCfg<KeyT, ValT, kThreads, kItems>;
   constexpr int kWarps = Cfg::kWarps;
   constexpr bool kEarlyVals = Cfg::kSeparate && sizeof(ValT) <= 8;
@@ -166,10 +180,16 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, k
   KeyT key[kItems];
   ValT val[kItems];
   unsigned slot[kItems];  // rank among equal digits of the warp -> tile-sorted position
+  if (kPrefetch && prefetched) {
+    asm volatile("cp.async.wait_all;" ::: "memory");  // own copies only: each thread reads what it fetched
 #pragma unroll
-  for (int t = 0; t < kItems; ++t) {
-    const unsigned off = warp_first + t * 32;
-    key[t] = (kFull || off < valid) ? src.key(tile + off) : KeyT(0);
+    for (int t = 0; t < kItems; ++t) key[t] = sm.prefetch[t * kThreads + tid];
+  } else {
+#pragma unroll
+    for (int t = 0; t < kItems; ++t) {
+      const unsigned off = warp_first + t * 32;
+      key[t] = (kFull || off < valid) ? src.key(tile + off) : KeyT(0);
+    }
   }
   if (kEarlyVals) {
 #pragma unroll
@@ -239,6 +259,22 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, k
       if (kEarlyVals) stage_vals[slot[t]] = val[t];
     }
   }
+  if constexpr (kPrefetch) {
+    if (next_valid) {  // next tile's keys travel while this tile is written out
+#pragma unroll
+      for (int t = 0; t < kItems; ++t) {
+        const unsigned off = warp_first + t * 32;
+        if (off < next_valid) {
+          const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(&sm.prefetch[t * kThreads + tid]));
+          asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src.key_ptr(next_tile + off)),
+                       "n"(sizeof(KeyT))
+                       : "memory");
+        } else {
+          sm.prefetch[t * kThreads + tid] = KeyT(0);
+        }
+      }
+    }
+  }
   if (!kEarlyVals) {  // the values are needed only after the keys have left; issue their loads now
 #pragma unroll
     for (int t = 0; t < kItems; ++t) {
@@ -288,7 +324,7 @@ __device__ __forceinline__ void scatter_tile(ScatterSmem<KeyT, ValT, kThreads, k
   }
 }
 
-template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks>
+template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks, bool kPrefetch>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src src, uint64_t n, uint64_t chunk,
                                                                     unsigned shift,
                                                                     const uint64_t* __restrict__ hist,
@@ -296,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src
                                                                     KeyT* __restrict__ keys_out,
                                                                     ValT* __restrict__ vals_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using Smem = ScatterSmem<KeyT, ValT, kThreads, kItems>;
+  using Smem = ScatterSmem<KeyT, ValT, kThreads, kItems, kPrefetch>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   constexpr int kTile = kThreads * kItems;
   const unsigned tid = threadIdx.x;
@@ -319,18 +355,26 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) radix_scatter_kernel(Src
   for (uint64_t ti = blockIdx.x; ti < full_tiles; ti += gridDim.x) {
     __syncthreads();
     if (tid < kRadixSize) sm.run_base[tid] = digit_base[tid] + ti * (kTile / kRadixSize);
-    scatter_tile<true, KeyT, ValT, Src, kThreads, kItems>(sm, src, ti * kTile, kTile, shift, keys_out, vals_out);
+    scatter_tile<true, false, KeyT, ValT, Src, kThreads, kItems>(
+        *reinterpret_cast<ScatterSmem<KeyT, ValT, kThreads, kItems, false>*>(smem_raw), src, ti * kTile, kTile, shift,
+        keys_out, vals_out, false, 0, 0);
   }
   (void)chunk;
 #else
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;
   const uint64_t end = begin + chunk < n ? begin + chunk : n;
   uint64_t tile = begin;
-  for (; tile + kTile <= end; tile += kTile)
-    scatter_tile<true, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, kTile, shift, keys_out, vals_out);
+  bool prefetched = false;
+  for (; tile + kTile <= end; tile += kTile) {
+    const uint64_t next = tile + kTile;
+    const unsigned next_valid = next < end ? static_cast<unsigned>(end - next < kTile ? end - next : kTile) : 0u;
+    scatter_tile<true, kPrefetch, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, kTile, shift, keys_out, vals_out,
+                                                                    prefetched, next, next_valid);
+    prefetched = kPrefetch && next_valid != 0;
+  }
   if (tile < end)
-    scatter_tile<false, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, static_cast<unsigned>(end - tile), shift,
-                                                          keys_out, vals_out);
+    scatter_tile<false, kPrefetch, KeyT, ValT, Src, kThreads, kItems>(sm, src, tile, static_cast<unsigned>(end - tile),
+                                                                     shift, keys_out, vals_out, prefetched, 0, 0);
 #endif
 }
 
@@ -380,7 +424,7 @@ struct RadixScratch {
   DevBuf<uint64_t> hist;         // [256][blocks]
   DevBuf<uint64_t> digit_total;  // [256]
   unsigned max_blocks = 0;
-  int variant = 1;  // scatter layout: 0 = 256 threads x 16 items, 1 = 512 x 8 (default; measured: profiles/r01)
+  int variant = 0;  // tools/radix_bench.cu only: 0 = the product choice (launch_scatter)
   int device = 0;
   KernelTimer timer;
   void init(const DeviceInfo& dev, cudaStream_t stream) {
@@ -394,35 +438,44 @@ struct RadixScratch {
   }
 };
 
-template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks>
+template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinBlocks, bool kPrefetch>
 inline void launch_scatter_variant(cudaStream_t stream, RadixScratch& rs, const Chunking& ck, Src src, uint64_t n,
                                    unsigned shift, KeyT* keys_out, ValT* vals_out) {
-  constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT, kThreads, kItems>);
+  constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT, kThreads, kItems, kPrefetch>);
   static bool configured[64] = {};  // per template instantiation and device (the attribute is per context)
   const int slot = rs.device & 63;
   if (!configured[slot] || rs.device >= 64) {
-    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks>,
+    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks, kPrefetch>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
     configured[slot] = true;
   }
-  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks>), ck.blocks, kThreads, kSmem, stream,
-               src, n, ck.chunk, shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
+  CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks, kPrefetch>), ck.blocks, kThreads,
+               kSmem, stream, src, n, ck.chunk, shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
 }
 
 template <class KeyT, class ValT, class Src>
 inline void launch_scatter(cudaStream_t stream, RadixScratch& rs, const Chunking& ck, Src src, uint64_t n,
                            unsigned shift, KeyT* keys_out, ValT* vals_out) {
   // wide elements: one CTA per SM is all the shared memory allows
-  constexpr int kMin = (sizeof(KeyT) + sizeof(ValT)) * kRsTile <= 96 * 1024 ? 2 : 1;
+  constexpr int kMin = (sizeof(KeyT) + sizeof(ValT)) * 4096 <= 96 * 1024 ? 2 : 1;
+  // asynchronous key prefetch where the keys are plain memory and the extra staging area fits
+  constexpr bool kPre = HasDirectKeys<Src>::value && (2 * sizeof(KeyT) + sizeof(ValT)) * 4096 <= 80 * 1024;
 #ifdef CAPSB_RADIX_ALL_VARIANTS  // tools/radix_bench.cu
   switch (rs.variant) {
-    case 0: launch_scatter_variant<KeyT, ValT, Src, 256, 16, kMin>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
-    case 2: launch_scatter_variant<KeyT, ValT, Src, 1024, 4, 1>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
-    case 3: launch_scatter_variant<KeyT, ValT, Src, 512, 8, 1>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 1: launch_scatter_variant<KeyT, ValT, Src, 512, 8, kMin, false>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 2: launch_scatter_variant<KeyT, ValT, Src, 256, 16, kMin, false>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 3: launch_scatter_variant<KeyT, ValT, Src, 256, 16, kMin, kPre>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 4: launch_scatter_variant<KeyT, ValT, Src, 1024, 8, 1, false>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
+    case 5: launch_scatter_variant<KeyT, ValT, Src, 512, 16, 1, false>(stream, rs, ck, src, n, shift, keys_out, vals_out); return;
     default: break;
   }
 #endif
-  launch_scatter_variant<KeyT, ValT, Src, 512, 8, kMin>(stream, rs, ck, src, n, shift, keys_out, vals_out);
+  // Measured (profiles/r01, 400 M (u64, u32) pairs): with the asynchronous key prefetch the
+  // 512 x 8 layout is the fastest (3.02 TB/s); without it 256 x 16 is (2.96 vs 2.70 TB/s).
+  if constexpr (kPre)
+    launch_scatter_variant<KeyT, ValT, Src, 512, 8, kMin, true>(stream, rs, ck, src, n, shift, keys_out, vals_out);
+  else
+    launch_scatter_variant<KeyT, ValT, Src, 256, 16, kMin, false>(stream, rs, ck, src, n, shift, keys_out, vals_out);
 }
 
 // One stable counting pass on the 8-bit digit at `shift`.

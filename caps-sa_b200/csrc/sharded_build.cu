@@ -132,17 +132,18 @@ struct ShardedRanks {
   const uint64_t* bucket_keys;     // this rank's sorted bucket
   uint64_t bucket_count, bucket_offset;
   uint64_t lo;              // first text position of this rank's slice
+  uint64_t slice_len = 0;
   DevBuf<IdxT> isa_local;
 
   ShardedRanks(Engine& e, Comm& c, SliceMap m, const PackedText& text, uint64_t mask, const uint64_t* samples,
                uint64_t stride, const uint64_t* keys, uint64_t count, uint64_t offset)
       : eng(e), comm(c), map(m), pt(text), key_mask(mask), sorted_samples(samples), sample_stride(stride),
         bucket_keys(keys), bucket_count(count), bucket_offset(offset), lo(m.begin(static_cast<unsigned>(c.rank))) {
-    const uint64_t slice = m.end(static_cast<unsigned>(c.rank)) - lo;
-    isa_local.alloc(slice ? slice : 1, e.stream);
+    slice_len = m.end(static_cast<unsigned>(c.rank)) - lo;  // isa_local is allocated by reset()
   }
 
   void reset() {
+    if (!isa_local) isa_local.alloc(slice_len ? slice_len : 1, eng.stream);
     CAPSB_CUDA(cudaMemsetAsync(isa_local.get(), 0xFF, isa_local.size() * sizeof(IdxT), eng.stream));
   }
 
@@ -189,14 +190,13 @@ struct ShardedRanks {
                                   [=] __device__(uint64_t t, IdxPair<IdxT> a) { answer[t] = a; });
   }
 
-  void make_comp(const IdxT* idx, const IdxT* group, uint64_t m, uint64_t h, Comp* comp) {
-    constexpr unsigned kField = IdxTraits<IdxT>::kField;
+  // second_out[t] = rank of suffix idx[t] + h, or n - 1 - idx[t] beyond the end of the text
+  void second_ranks(const IdxT* idx, uint64_t m, uint64_t h, IdxT* second_out) {
     cudaStream_t st = eng.stream;
     const SliceMap mp = map;
     const uint64_t n = map.n, lo_ = lo;
     const unsigned self = static_cast<unsigned>(comm.rank);
-    DevBuf<IdxT> second(m, st);
-    IdxT* sec = second.get();
+    IdxT* sec = second_out;
 
     // 1. ask the owner of text position i + h for its rank.  Suffixes that run past the end
     //    need none; they ride along as a request to this rank.
@@ -273,9 +273,7 @@ struct ShardedRanks {
 
     launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
       const uint64_t i = idx[t];
-      const bool inside = i + h < n;
-      const uint64_t s2 = inside ? static_cast<uint64_t>(sec[t]) : (n - 1 - i);
-      comp[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) | static_cast<Comp>(s2);
+      if (i + h >= n) sec[t] = static_cast<IdxT>(n - 1 - i);
     });
   }
 };
@@ -315,6 +313,31 @@ __global__ void __launch_bounds__(256) locate_pivots_kernel(const uint64_t* __re
 
 constexpr unsigned kSamplesPerRank = 1024;
 
+// Partition pass of the partition-first mode: "digit" = the bucket the suffix belongs to
+// (number of pivots below its key: keys <= pivot j go to ranks <= j), value = the suffix.
+template <class IdxT>
+struct BucketSource {
+  PackedText pt;
+  uint64_t mask;
+  uint64_t base;
+  const uint64_t* pivot;  // pivots[0 .. pivots)
+  unsigned pivots;
+  __device__ __forceinline__ uint8_t key(uint64_t i) const {
+    const uint64_t k = pt.window(base + i) & mask;
+    unsigned lo = 0, hi = pivots;  // first pivot that is >= k
+    while (lo < hi) {
+      const unsigned mid = (lo + hi) >> 1;
+      if (pivot[mid] < k)
+        lo = mid + 1;
+      else
+        hi = mid;
+    }
+    return static_cast<uint8_t>(lo);
+  }
+  __device__ __forceinline__ IdxT val(uint64_t i) const { return static_cast<IdxT>(base + i); }
+  static constexpr uint64_t bytes_read_per_item() { return 1; }
+};
+
 }  // namespace
 
 template <class IdxT>
@@ -347,73 +370,139 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   eng.stats.alphabet_size = packed.sigma;
   clock.mark("packed");  // 1
 
-  // ---- slice sort ------------------------------------------------------------------------
   const SliceMap map{n, n / world, world};
   const uint64_t lo = map.begin(rank);
   const uint64_t slice_count = map.end(rank) - lo;
   const unsigned key_bits = choose_key_bits(n);
+  const uint64_t key_mask = key_mask_of(key_bits);
   eng.stats.key_bits = key_bits;
-  DevBuf<uint64_t> slice_keys(slice_count, st);
-  DevBuf<IdxT> slice_idx(slice_count, st);
-  sort_suffix_slice<IdxT>(eng, pt, lo, slice_count, key_bits, slice_keys.get(), slice_idx.get());
-  clock.mark("slice sorted");  // 2
+  // CAPSB_SHARD_MODE=merge: the reference's order of stages (sort the slices, exchange sorted
+  // runs, merge).  Default: partition first (exchange suffix indices only, sort the bucket) —
+  // no merge passes and a third of the NVLink bytes.
+  const char* mode_env = std::getenv("CAPSB_SHARD_MODE");  // read per construction: the tests flip it
+  const bool merge_mode = mode_env && std::string(mode_env) == "merge";
+  if (world > static_cast<unsigned>(kRadixSize)) fail("more ranks than the bucket digit can hold");
 
-  // ---- pivots: regular samples, all-gather, every rank sorts the same sample set ----------
   const uint64_t sample_total = static_cast<uint64_t>(kSamplesPerRank) * world;
   DevBuf<uint64_t> samples(kSamplesPerRank, st), all_a(sample_total, st), all_b(sample_total, st);
   DevBuf<uint32_t> dummy_a(sample_total, st), dummy_b(sample_total, st);
-  CAPSB_CUDA(cudaMemsetAsync(dummy_a.get(), 0, sample_total * sizeof(uint32_t), st));
-  {
-    uint64_t* s = samples.get();
-    const uint64_t* k = slice_keys.get();
-    launch_map(dev, st, kSamplesPerRank, [=] __device__(uint64_t t) {
-      // regular sampling (reference sample_pivots, src/Suffix_Array.cpp:187-194); an empty
-      // slice contributes the largest key so it does not pull the pivots down
-      s[t] = slice_count ? k[((t + 1) * slice_count + kSamplesPerRank - 1) / kSamplesPerRank - 1] : ~0ull;
-    });
-  }
-  comm.all_gather_device(samples.get(), all_a.get(), kSamplesPerRank * sizeof(uint64_t), st);
-  const int sorted_in_b = radix_sort_pairs<uint64_t, uint32_t>(st, eng.radix, all_a.get(), dummy_a.get(), all_b.get(),
-                                                              dummy_b.get(), sample_total, 64 - key_bits, 64);
-  const uint64_t* sorted_samples = sorted_in_b ? all_b.get() : all_a.get();
-
-  // ---- locate the pivots in the sorted slice -> send counts -> the G x G count matrix ------
-  DevBuf<uint64_t> d_bounds(world + 1, st);
-  {
-    const unsigned pivots = world - 1;
-    const unsigned blocks = pivots ? static_cast<unsigned>(ceil_div(pivots, 8)) : 1;
-    CAPSB_LAUNCH(locate_pivots_kernel, blocks, 256, 0, st, slice_keys.get(), slice_count, sorted_samples,
-                 static_cast<uint64_t>(kSamplesPerRank), pivots, d_bounds.get());
-  }
-  std::vector<uint64_t> bounds(world + 1);
-  CAPSB_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.get(), (world + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-  CAPSB_CUDA(cudaStreamSynchronize(st));
+  const uint64_t* sorted_samples = nullptr;
+  // every rank sorts the same all-gathered sample set and so picks the same G-1 pivots
+  // (reference select_pivots, src/Suffix_Array.cpp:197-222): pivot j = sorted_samples[(j+1)*1024 - 1]
+  auto agree_on_pivots = [&]() {
+    CAPSB_CUDA(cudaMemsetAsync(dummy_a.get(), 0, sample_total * sizeof(uint32_t), st));
+    comm.all_gather_device(samples.get(), all_a.get(), kSamplesPerRank * sizeof(uint64_t), st);
+    const int sorted_in_b = radix_sort_pairs<uint64_t, uint32_t>(st, eng.radix, all_a.get(), dummy_a.get(), all_b.get(),
+                                                                dummy_b.get(), sample_total, 64 - key_bits, 64);
+    sorted_samples = sorted_in_b ? all_b.get() : all_a.get();
+  };
   std::vector<uint64_t> send_counts(world), recv_counts(world), matrix(static_cast<size_t>(world) * world);
-  for (unsigned p = 0; p < world; ++p) send_counts[p] = bounds[p + 1] - bounds[p];
-  comm.all_gather_host(send_counts.data(), world * sizeof(uint64_t), matrix.data(), st);
   uint64_t bucket_count = 0, bucket_offset = 0;
-  for (unsigned s = 0; s < world; ++s) {
-    recv_counts[s] = matrix[static_cast<size_t>(s) * world + rank];
-    bucket_count += recv_counts[s];
-    for (unsigned q = 0; q < rank; ++q) bucket_offset += matrix[static_cast<size_t>(s) * world + q];
-  }
-  out.offset = bucket_offset;
-  out.count = bucket_count;
-  eng.stats.shard_offset = bucket_offset;
-  eng.stats.shard_count = bucket_count;
+  // all-gather of the send counts -> the G x G count matrix (the reference's P, :481) -> what
+  // this rank receives and where its bucket starts in the suffix array (part_size_scan_, :319-330)
+  auto exchange_counts = [&]() {
+    comm.all_gather_host(send_counts.data(), world * sizeof(uint64_t), matrix.data(), st);
+    for (unsigned s = 0; s < world; ++s) {
+      recv_counts[s] = matrix[static_cast<size_t>(s) * world + rank];
+      bucket_count += recv_counts[s];
+      for (unsigned q = 0; q < rank; ++q) bucket_offset += matrix[static_cast<size_t>(s) * world + q];
+    }
+    out.offset = bucket_offset;
+    out.count = bucket_count;
+    eng.stats.shard_offset = bucket_offset;
+    eng.stats.shard_count = bucket_count;
+  };
+  DevBuf<uint64_t> bucket_keys;
 
-  // ---- collate: (key, suffix) runs move to the rank that owns their bucket -----------------
-  DevBuf<uint64_t> bucket_keys(bucket_count, st), bucket_keys_tmp(bucket_count, st);
-  DevBuf<IdxT> bucket_idx_tmp(bucket_count, st);
-  out.sa.alloc(bucket_count, st);
-  comm.all_to_all_v(slice_keys.get(), send_counts.data(), bucket_keys.get(), recv_counts.data(), sizeof(uint64_t), st);
-  comm.all_to_all_v(slice_idx.get(), send_counts.data(), out.sa.get(), recv_counts.data(), sizeof(IdxT), st);
-  slice_keys.release();
-  slice_idx.release();
-  clock.mark("exchanged");  // 3
+  if (!merge_mode) {
+    // ---- pivots from a sample of this rank's slice of the text --------------------------------
+    {
+      uint64_t* s = samples.get();
+      const PackedText text = pt;
+      launch_map(dev, st, kSamplesPerRank, [=] __device__(uint64_t t) {
+        // scrambled positions (a regular stride could alias with a periodic text); an empty
+        // slice contributes the largest key so it does not pull the pivots down
+        uint64_t z = (t + 1) * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
+        z ^= z >> 32;
+        s[t] = slice_count ? (text.window(lo + z % slice_count) & key_mask) : ~0ull;
+      });
+    }
+    agree_on_pivots();
+    DevBuf<uint64_t> pivots(world, st);
+    {
+      uint64_t* pv = pivots.get();
+      const uint64_t* ss = sorted_samples;
+      launch_map(dev, st, world - 1, [=] __device__(uint64_t j) { pv[j] = ss[(j + 1) * kSamplesPerRank - 1]; });
+    }
+    // ---- partition: the slice's suffixes grouped by bucket, in text order inside a bucket ----
+    DevBuf<IdxT> slice_idx(slice_count, st);
+    {
+      DevBuf<uint8_t> bucket_of(slice_count, st);
+      CAPSB_CUDA(cudaMemsetAsync(eng.radix.digit_total.get(), 0, kRadixSize * sizeof(uint64_t), st));
+      radix_pass<uint8_t, IdxT>(st, eng.radix, BucketSource<IdxT>{pt, key_mask, lo, pivots.get(), world - 1},
+                                slice_count, 0, bucket_of.get(), slice_idx.get());
+      CAPSB_CUDA(cudaMemcpyAsync(send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t),
+                                 cudaMemcpyDeviceToHost, st));
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+    }
+    exchange_counts();
+    clock.mark("partitioned");  // 2
+    // ---- collate: suffix indices move to the rank that owns their bucket ----------------------
+    DevBuf<IdxT> bucket_idx(bucket_count, st);
+    comm.all_to_all_v(slice_idx.get(), send_counts.data(), bucket_idx.get(), recv_counts.data(), sizeof(IdxT), st);
+    slice_idx.release();
+    clock.mark("exchanged");  // 3
+    // ---- bucket sort: keys come from the text again (each received run is in text order) ------
+    bucket_keys.alloc(bucket_count, st);
+    out.sa.alloc(bucket_count, st);
+    sort_suffixes_by_key<IdxT>(eng, SuffixListSource<IdxT>{pt, key_mask, bucket_idx.get()}, bucket_count, key_bits,
+                               bucket_keys.get(), out.sa.get());
+    clock.mark("bucket sorted");  // 4
+  } else {
+    // ---- slice sort ------------------------------------------------------------------------
+    DevBuf<uint64_t> slice_keys(slice_count, st);
+    DevBuf<IdxT> slice_idx(slice_count, st);
+    sort_suffix_slice<IdxT>(eng, pt, lo, slice_count, key_bits, slice_keys.get(), slice_idx.get());
+    clock.mark("slice sorted");  // 2
 
-  // ---- bucket merge ------------------------------------------------------------------------
-  {
+    // ---- pivots: regular samples of the sorted slice (reference sample_pivots, :187-194) ------
+    {
+      uint64_t* s = samples.get();
+      const uint64_t* k = slice_keys.get();
+      launch_map(dev, st, kSamplesPerRank, [=] __device__(uint64_t t) {
+        // an empty slice contributes the largest key so it does not pull the pivots down
+        s[t] = slice_count ? k[((t + 1) * slice_count + kSamplesPerRank - 1) / kSamplesPerRank - 1] : ~0ull;
+      });
+    }
+    agree_on_pivots();
+
+    // ---- locate the pivots in the sorted slice -> send counts ----------------------------------
+    DevBuf<uint64_t> d_bounds(world + 1, st);
+    {
+      const unsigned pivots = world - 1;
+      const unsigned blocks = pivots ? static_cast<unsigned>(ceil_div(pivots, 8)) : 1;
+      CAPSB_LAUNCH(locate_pivots_kernel, blocks, 256, 0, st, slice_keys.get(), slice_count, sorted_samples,
+                   static_cast<uint64_t>(kSamplesPerRank), pivots, d_bounds.get());
+    }
+    std::vector<uint64_t> bounds(world + 1);
+    CAPSB_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.get(), (world + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    for (unsigned p = 0; p < world; ++p) send_counts[p] = bounds[p + 1] - bounds[p];
+    exchange_counts();
+
+    // ---- collate: (key, suffix) runs move to the rank that owns their bucket -----------------
+    DevBuf<uint64_t> bucket_keys_tmp(bucket_count, st);
+    DevBuf<IdxT> bucket_idx_tmp(bucket_count, st);
+    bucket_keys.alloc(bucket_count, st);
+    out.sa.alloc(bucket_count, st);
+    comm.all_to_all_v(slice_keys.get(), send_counts.data(), bucket_keys.get(), recv_counts.data(), sizeof(uint64_t), st);
+    comm.all_to_all_v(slice_idx.get(), send_counts.data(), out.sa.get(), recv_counts.data(), sizeof(IdxT), st);
+    slice_keys.release();
+    slice_idx.release();
+    clock.mark("exchanged");  // 3
+
+    // ---- bucket merge ------------------------------------------------------------------------
     std::vector<uint64_t> offsets(world + 1, 0);
     for (unsigned s = 0; s < world; ++s) offsets[s + 1] = offsets[s] + recv_counts[s];
     const int in_tmp = merge_sorted_runs<uint64_t, IdxT>(dev, st, bucket_keys.get(), out.sa.get(),
@@ -422,12 +511,10 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
       std::swap(bucket_keys, bucket_keys_tmp);
       std::swap(out.sa, bucket_idx_tmp);
     }
+    clock.mark("merged");  // 4
   }
-  bucket_keys_tmp.release();
-  bucket_idx_tmp.release();
   const uint64_t* keys = bucket_keys.get();
   IdxT* d_sa = out.sa.get();
-  clock.mark("merged");  // 4
 
   // ---- ties (collective: every rank runs the same number of rounds) ---------------------------
   out.lcp.alloc(bucket_count, st);
@@ -510,9 +597,15 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   CAPSB_CUDA(cudaStreamSynchronize(st));
 
   eng.stats.ms_pack = clock.between(0, 1);
-  eng.stats.ms_sort = clock.between(1, 2);
-  eng.stats.ms_partition = clock.between(2, 3);
-  eng.stats.ms_merge = clock.between(3, 4);
+  if (merge_mode) {
+    eng.stats.ms_sort = clock.between(1, 2);
+    eng.stats.ms_partition = clock.between(2, 3);
+    eng.stats.ms_merge = clock.between(3, 4);
+  } else {
+    eng.stats.ms_partition = clock.between(1, 3);  // pivots, partition pass, suffix all-to-all
+    eng.stats.ms_sort = clock.between(3, 4);       // bucket sort
+    eng.stats.ms_merge = 0;
+  }
   eng.stats.ms_refine = clock.between(4, 5);
   eng.stats.ms_deep_lcp = clock.between(5, 6);
   eng.stats.ms_total = clock.between(0, 6);

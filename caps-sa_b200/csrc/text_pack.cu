@@ -13,12 +13,11 @@ namespace {
 
 __global__ void __launch_bounds__(256) alphabet_scan_kernel(const uint8_t* __restrict__ text,
                                                             uint64_t n, uint32_t* present /*[8]*/) {
-  uint32_t seen[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  auto note = [&](uint32_t byte) {
-    // branch-free update of an 8-register bitmap
-#pragma unroll
-    for (int k = 0; k < 8; ++k) seen[k] |= (byte >> 5) == static_cast<uint32_t>(k) ? (1u << (byte & 31u)) : 0u;
-  };
+  // one flag byte per byte value in shared memory: a plain store per input byte (lanes that
+  // hit the same word merge), no read-modify-write and no per-thread bitmap arithmetic
+  __shared__ uint8_t seen[256];
+  seen[threadIdx.x] = 0;
+  __syncthreads();
   const uint64_t gtid = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint64_t gsize = static_cast<uint64_t>(gridDim.x) * blockDim.x;
   const bool aligned = (reinterpret_cast<uintptr_t>(text) & 15u) == 0;
@@ -27,23 +26,22 @@ __global__ void __launch_bounds__(256) alphabet_scan_kernel(const uint8_t* __res
     const uint64_t nvec = n / 16;
     vec_end = nvec * 16;
     const uint4* v = reinterpret_cast<const uint4*>(text);
-    for (uint64_t i = gtid; i < nvec; i += gsize) {
-      const uint4 q = __ldg(v + i);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+    for (uint64_t i = gtid; i < nvec; i += 2 * gsize) {
+      const uint64_t j = i + gsize;
+      const uint4 q0 = __ldg(v + i);
+      const uint4 q1 = __ldg(v + (j < nvec ? j : i));
+      const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < 8; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) note((w[a] >> (8 * b)) & 0xFFu);
+        for (int b = 0; b < 4; ++b) seen[(w[a] >> (8 * b)) & 0xFFu] = 1;
     }
   }
-  for (uint64_t i = vec_end + gtid; i < n; i += gsize) note(text[i]);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t v = seen[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
-    if (lane_id() == 0 && v) atomicOr(present + k, v);
-  }
+  for (uint64_t i = vec_end + gtid; i < n; i += gsize) seen[text[i]] = 1;
+  __syncthreads();
+  const unsigned mine = seen[threadIdx.x] ? 1u : 0u;
+  const unsigned word = __ballot_sync(0xffffffffu, mine);  // warp w covers byte values 32w .. 32w+31
+  if (lane_id() == 0 && word) atomicOr(present + (threadIdx.x >> 5), word);
 }
 
 // One thread builds one 64-bit output word from S = 64 >> LOG2BITS input bytes.

@@ -86,6 +86,19 @@ def test_sharded_tiny_inputs(pkg, ranks):
         assert np.array_equal(obj.LCP(), nlcp.astype(np.uint32)), raw
 
 
+@pytest.mark.parametrize("ranks", [2, 3, 8])
+@pytest.mark.parametrize("case", ["acgt_1M", "genome_like_2M", "bytes256_300k", "fibonacci_200k", "allA_50k"])
+def test_sharded_merge_mode_matches_oracle(pkg, synth, case, ranks, monkeypatch):
+    """CAPSB_SHARD_MODE=merge: the reference's order of stages (slice sort, pivot location in the
+    sorted slices, exchange of sorted runs, merge-path bucket merge) instead of partition-first."""
+    monkeypatch.setenv("CAPSB_SHARD_MODE", "merge")
+    text, want_sa, want_lcp = oracle(case, synth)
+    obj = pkg.SuffixArray(text, devices=device_list(pkg, ranks))
+    obj.construct()
+    assert any(s["ms_merge"] > 0 for s in obj._rank_stats)
+    assert np.array_equal(obj.SA(), want_sa) and np.array_equal(obj.LCP(), want_lcp)
+
+
 def test_sharded_equals_single_device_path(pkg, synth):
     text = synth.genome_like(5_000_000, seed=7, scale=0.01)
     one = pkg.SuffixArray(text)

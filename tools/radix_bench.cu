@@ -43,8 +43,8 @@ int main(int argc, char** argv) {
     rs.timer.enabled = true;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0), cudaEventCreate(&e1);
-    const char* names[] = {"256x16 mb2", "512x8 mb2", "1024x4 mb1", "512x8 mb1"};
-    for (int variant = 0; variant < 4; ++variant) {
+    const char* names[] = {"512x8 prefetch (product)", "512x8", "256x16", "256x16 prefetch", "1024x8 tile 8192", "512x16 tile 8192"};
+    for (int variant = 0; variant < 6; ++variant) {
       if (argc > 4 && atoi(argv[4]) != variant) continue;
       rs.variant = variant;
       for (int w = 0; w < 3; ++w)
