@@ -1,6 +1,7 @@
 // C-ABI layer (include/caps_sa_gpu.h): argument checks, host<->device staging, and the
 // translation of capsb::Error into return codes.  No CPU fallback anywhere: without a CUDA
 // device every entry point fails loudly.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <thread>
@@ -61,6 +62,45 @@ struct EventPair {
   }
 };
 
+// Host-buffer entry points: while in scope, the engine copies the suffix array to `sa_out` as
+// soon as it is final (Engine::sa_is_final); finish() copies the rest once the construction is
+// done.  All copies run on the engine's copy stream.
+template <class IdxT>
+struct ResultCopy {
+  Engine& eng;
+  EventPair d2h;
+  ResultCopy(Engine& e, IdxT* sa_out) : eng(e) {
+    // CAPSB_EARLY_SA=0: measurement switch, both copies after the construction
+    const char* env = std::getenv("CAPSB_EARLY_SA");
+    eng.sa_sink = (env && env[0] == '0') ? nullptr : sa_out;
+    eng.sa_sink_started = d2h.a;
+    eng.sa_sunk = false;
+  }
+  ~ResultCopy() {
+    eng.sa_sink = nullptr;
+    eng.sa_sink_started = nullptr;
+    cudaStreamSynchronize(eng.copy_stream);  // no copy into the caller's arrays outlives the call
+  }
+  // d_sa / d_lcp [0, count) = entries [first, first + count) of the full arrays
+  void finish(const IdxT* d_sa, const IdxT* d_lcp, IdxT* sa_out, IdxT* lcp_out, uint64_t first, uint64_t count) {
+    cudaStream_t cs = eng.copy_stream;
+    eng.sa_sink = nullptr;
+    CAPSB_CUDA(cudaEventRecord(d2h.b, eng.stream));
+    CAPSB_CUDA(cudaStreamWaitEvent(cs, d2h.b, 0));
+    if (!eng.sa_sunk) {
+      CAPSB_CUDA(cudaEventRecord(d2h.a, cs));
+      if (count)
+        CAPSB_CUDA(cudaMemcpyAsync(sa_out + first, d_sa, count * sizeof(IdxT), cudaMemcpyDeviceToHost, cs));
+    }
+    if (count)
+      CAPSB_CUDA(cudaMemcpyAsync(lcp_out + first, d_lcp, count * sizeof(IdxT), cudaMemcpyDeviceToHost, cs));
+    CAPSB_CUDA(cudaEventRecord(d2h.b, cs));
+    CAPSB_CUDA(cudaStreamSynchronize(cs));
+    CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+    eng.stats.ms_d2h = d2h.ms();
+  }
+};
+
 template <class IdxT>
 int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, IdxT* sa_out, IdxT* lcp_out,
                    uint64_t max_context) {
@@ -79,18 +119,14 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
     cudaStream_t st = eng.stream;
     capsb::DevBuf<uint8_t> d_text(n, st);
     capsb::DevBuf<IdxT> d_sa(n, st), d_lcp(n, st);
-    EventPair h2d, d2h;
+    EventPair h2d;
+    ResultCopy<IdxT> results(eng, sa_out);
     CAPSB_CUDA(cudaEventRecord(h2d.a, st));
     CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
     CAPSB_CUDA(cudaEventRecord(h2d.b, st));
     capsb::build_sa_lcp<IdxT>(eng, d_text.get(), n, d_sa.get(), d_lcp.get());
-    CAPSB_CUDA(cudaEventRecord(d2h.a, st));
-    CAPSB_CUDA(cudaMemcpyAsync(sa_out, d_sa.get(), n * sizeof(IdxT), cudaMemcpyDeviceToHost, st));
-    CAPSB_CUDA(cudaMemcpyAsync(lcp_out, d_lcp.get(), n * sizeof(IdxT), cudaMemcpyDeviceToHost, st));
-    CAPSB_CUDA(cudaEventRecord(d2h.b, st));
-    CAPSB_CUDA(cudaStreamSynchronize(st));
+    results.finish(d_sa.get(), d_lcp.get(), sa_out, lcp_out, 0, n);
     eng.stats.ms_h2d = h2d.ms();
-    eng.stats.ms_d2h = d2h.ms();
     return CAPS_SA_GPU_OK;
   });
 }
@@ -200,22 +236,13 @@ int construct_multi(const int* devices, int num_ranks, const char* text, uint64_
           if (n) {
             cudaStream_t st = eng.stream;
             capsb::ShardResult<IdxT> shard;
+            ResultCopy<IdxT> results(eng, sa_out);
             {
               StagedText staged = stage_text_sharded(eng, comm, text, n);
               capsb::build_sa_lcp_sharded<IdxT>(eng, comm, staged.buf.get(), n, shard);
               eng.stats.ms_h2d = staged.ms_h2d;
             }
-            EventPair d2h;
-            CAPSB_CUDA(cudaEventRecord(d2h.a, st));
-            if (shard.count) {
-              CAPSB_CUDA(cudaMemcpyAsync(sa_out + shard.offset, shard.sa.get(), shard.count * sizeof(IdxT),
-                                         cudaMemcpyDeviceToHost, st));
-              CAPSB_CUDA(cudaMemcpyAsync(lcp_out + shard.offset, shard.lcp.get(), shard.count * sizeof(IdxT),
-                                         cudaMemcpyDeviceToHost, st));
-            }
-            CAPSB_CUDA(cudaEventRecord(d2h.b, st));
-            CAPSB_CUDA(cudaStreamSynchronize(st));
-            eng.stats.ms_d2h = d2h.ms();
+            results.finish(shard.sa.get(), shard.lcp.get(), sa_out, lcp_out, shard.offset, shard.count);
           }
           stats[r] = eng.stats;
         } catch (const std::exception& e) {
@@ -260,23 +287,14 @@ int construct_sharded_host(caps_sa_gpu_engine* engine, const char* text, uint64_
     cudaStream_t st = eng.stream;
     capsb::ShardResult<IdxT>& shard = shard_of<IdxT>(eng);
     float ms_h2d = 0;
+    ResultCopy<IdxT> results(eng, sa_out);
     {
       StagedText staged = stage_text_sharded(eng, *eng.comm, text, n);
       capsb::build_sa_lcp_sharded<IdxT>(eng, *eng.comm, staged.buf.get(), n, shard);
       ms_h2d = staged.ms_h2d;
     }
-    EventPair d2h;
-    CAPSB_CUDA(cudaEventRecord(d2h.a, st));
-    if (shard.count) {
-      CAPSB_CUDA(cudaMemcpyAsync(sa_out + shard.offset, shard.sa.get(), shard.count * sizeof(IdxT),
-                                 cudaMemcpyDeviceToHost, st));
-      CAPSB_CUDA(cudaMemcpyAsync(lcp_out + shard.offset, shard.lcp.get(), shard.count * sizeof(IdxT),
-                                 cudaMemcpyDeviceToHost, st));
-    }
-    CAPSB_CUDA(cudaEventRecord(d2h.b, st));
-    CAPSB_CUDA(cudaStreamSynchronize(st));
+    results.finish(shard.sa.get(), shard.lcp.get(), sa_out, lcp_out, shard.offset, shard.count);
     eng.stats.ms_h2d = ms_h2d;
-    eng.stats.ms_d2h = d2h.ms();
     return CAPS_SA_GPU_OK;
   });
 }

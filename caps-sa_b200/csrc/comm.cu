@@ -231,8 +231,7 @@ void NcclComm::all_gather_host(const void* in, size_t bytes, void* out, cudaStre
   DevBuf<unsigned char> d_in(bytes, st), d_out(bytes * static_cast<size_t>(world), st);
   CAPSB_CUDA(cudaMemcpyAsync(d_in.get(), in, bytes, cudaMemcpyHostToDevice, st));
   nccl_check(nccl().AllGather(d_in.get(), d_out.get(), bytes, kNcclUint8, comm_, st), "ncclAllGather");
-  CAPSB_CUDA(cudaMemcpyAsync(out, d_out.get(), bytes * static_cast<size_t>(world), cudaMemcpyDeviceToHost, st));
-  CAPSB_CUDA(cudaStreamSynchronize(st));
+  read_back(st, out, d_out.get(), bytes * static_cast<size_t>(world));
 }
 
 }  // namespace capsb

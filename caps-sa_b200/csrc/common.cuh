@@ -10,6 +10,7 @@
 //     contiguous chunks, so per-block partials stay small and scans are 3 short kernels.
 #pragma once
 
+#include <cstring>
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -308,6 +309,39 @@ __device__ __forceinline__ uint64_t ld_stream_u64(const uint64_t* p) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Small device -> host reads (counts, totals) that do not use the copy engine: a one-warp
+// kernel stores the words into mapped pinned host memory.  A cudaMemcpyAsync of a few bytes
+// queues behind whatever the device-to-host engine is busy with — the multi-GB copy of the
+// finished suffix array that overlaps the LCP stage (Engine::sa_is_final) stalled that stage
+// for its whole duration this way.  Synchronises the stream, like the copies it replaces.
+// ---------------------------------------------------------------------------------------
+static __global__ void mailbox_kernel(const uint32_t* __restrict__ src, volatile uint32_t* dst, unsigned words) {
+  for (unsigned i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
+inline void read_back(cudaStream_t stream, void* host_dst, const void* dev_src, size_t bytes) {
+  constexpr size_t kMailboxBytes = 4096;
+  if (bytes == 0) return;
+  if (bytes > kMailboxBytes || (bytes & 3u) || (reinterpret_cast<uintptr_t>(dev_src) & 3u)) {
+    CAPSB_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, stream));
+    CAPSB_CUDA(cudaStreamSynchronize(stream));
+    return;
+  }
+  struct Box {  // one per host thread (a thread drives one engine at a time)
+    void* p = nullptr;
+    ~Box() {
+      if (p) cudaFreeHost(p);
+    }
+  };
+  thread_local Box box;
+  if (!box.p) CAPSB_CUDA(cudaHostAlloc(&box.p, kMailboxBytes, cudaHostAllocPortable | cudaHostAllocMapped));
+  CAPSB_LAUNCH(mailbox_kernel, 1, 32, 0, stream, static_cast<const uint32_t*>(dev_src),
+               static_cast<volatile uint32_t*>(box.p), static_cast<unsigned>(bytes / 4));
+  CAPSB_CUDA(cudaStreamSynchronize(stream));
+  std::memcpy(host_dst, box.p, bytes);
+}
+
+// ---------------------------------------------------------------------------------------
 // Generic element-wise kernel: f(i) for i in [0, n), grid-stride.
 // ---------------------------------------------------------------------------------------
 template <class F>
@@ -558,9 +592,7 @@ inline void device_scan(const DeviceInfo& dev, cudaStream_t stream, ScanScratch<
   CAPSB_LAUNCH((scan_apply_kernel<T, Op, Inclusive, In, Out>), ck.blocks, kScanThreads, 0, stream, n,
                ck.chunk, in, out, scratch.partial.get());
   if (total_host) {
-    CAPSB_CUDA(cudaMemcpyAsync(total_host, scratch.total.get(), sizeof(T), cudaMemcpyDeviceToHost,
-                               stream));
-    CAPSB_CUDA(cudaStreamSynchronize(stream));
+    read_back(stream, total_host, scratch.total.get(), sizeof(T));
   }
 }
 

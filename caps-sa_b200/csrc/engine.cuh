@@ -66,6 +66,15 @@ struct Engine {
   ScanScratch<uint64_t> scan64;
   Stats stats;
   std::vector<cudaEvent_t> events;
+  // Host-buffer entry points: the suffix array is final once the ties are resolved, a stage
+  // before the LCP array, so its device-to-host copy starts there, on copy_stream, and overlaps
+  // the deep-LCP stage.  sa_sink = host array (indexed like the full SA), or null.
+  cudaStream_t copy_stream = nullptr;
+  void* sa_sink = nullptr;
+  cudaEvent_t sa_sink_started = nullptr;  // recorded on copy_stream right before the copy (caller-owned)
+  bool sa_sunk = false;
+  // d_sa[0, count) = SA[first, first + count) is final
+  void sa_is_final(const void* d_sa, uint64_t first, uint64_t count, size_t idx_bytes);
   // sharded construction (multi-process): the transport this engine joined and its last shard
   std::unique_ptr<Comm> comm;
   ShardResult<uint32_t> shard32;

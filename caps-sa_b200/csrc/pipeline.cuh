@@ -136,8 +136,7 @@ T scan_total(Engine& eng, uint64_t n, In in) {
   CAPSB_LAUNCH((scan_spine_kernel<T, Op>), 1, kScanThreads, 0, eng.stream, ck.blocks, sc.partial.get(),
                sc.total.get());
   T total;
-  CAPSB_CUDA(cudaMemcpyAsync(&total, sc.total.get(), sizeof(T), cudaMemcpyDeviceToHost, eng.stream));
-  CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+  read_back(eng.stream, &total, sc.total.get(), sizeof(T));
   return total;
 }
 // Must directly follow scan_total / another scan of the same n (reuses the partials).
@@ -317,6 +316,115 @@ constexpr unsigned kSmallGroup = 32;  // groups up to this size are ordered by c
 // d_lcp value of a position whose LCP is still to be computed (an LCP is at most n - 1)
 template <class IdxT>
 constexpr IdxT kLcpUnset = ~IdxT(0);
+
+// ---------------------------------------------------------------------------------------
+// First pass over the key-sorted suffixes (one streaming sweep, 128-bit accesses, four
+// consecutive positions per thread): writes the LCP of every position whose key differs from
+// its predecessor's (clz of the key XOR), marks the others unset, records in a bitmap which
+// positions sit in a key group of two or more (= still tied) and counts them per chunk, with
+// the chunking of the compaction that follows (select_finish), which then reads one bit per
+// position instead of the keys again.  Algorithmic traffic: 8 + w read, w written per suffix.
+// Entries next to a tied group are provisional (their bound depends on which member ends up at
+// the group's edge); refine_tied_groups rewrites them at the end.
+// ---------------------------------------------------------------------------------------
+constexpr int kKeyLcpThreads = 256;
+
+__device__ __forceinline__ void load4(const uint32_t* p, uint32_t (&v)[4]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+}
+__device__ __forceinline__ void load4(const uint64_t* p, uint64_t (&v)[4]) {
+  const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(p), b = *reinterpret_cast<const ulonglong2*>(p + 2);
+  v[0] = a.x, v[1] = a.y, v[2] = b.x, v[3] = b.y;
+}
+__device__ __forceinline__ void store4(uint32_t* p, const uint32_t (&v)[4]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void store4(uint64_t* p, const uint64_t (&v)[4]) {
+  *reinterpret_cast<ulonglong2*>(p) = make_ulonglong2(v[0], v[1]);
+  *reinterpret_cast<ulonglong2*>(p + 2) = make_ulonglong2(v[2], v[3]);
+}
+
+template <class IdxT>
+__global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uint64_t* __restrict__ keys,
+                                                                       const IdxT* __restrict__ sa,
+                                                                       IdxT* __restrict__ lcp,
+                                                                       uint32_t* __restrict__ tied_bits, uint64_t count,
+                                                                       uint64_t chunk, uint64_t n, unsigned log2_bits,
+                                                                       IdxT* __restrict__ partial) {
+  __shared__ unsigned warp_sums[kKeyLcpThreads / 32];
+  const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;  // a multiple of 128
+  const uint64_t end = begin + chunk < count ? begin + chunk : count;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned tied_here = 0;
+  for (uint64_t wbase = begin + warp * 128ull; wbase < end; wbase += (kKeyLcpThreads / 32) * 128ull) {
+    const uint64_t k0 = wbase + 4ull * lane;
+    uint64_t key[4];
+    IdxT s[4], l[4];
+    uint64_t prev_key, next_key;
+    IdxT prev_sa;
+    if (wbase + 128 <= end) {  // warp-uniform: the whole row of 128 positions exists
+      load4(keys + k0, key);
+      load4(sa + k0, s);
+      prev_key = __shfl_up_sync(0xffffffffu, key[3], 1);
+      prev_sa = __shfl_up_sync(0xffffffffu, s[3], 1);
+      next_key = __shfl_down_sync(0xffffffffu, key[0], 1);
+      if (lane == 0) {
+        prev_key = k0 > 0 ? keys[k0 - 1] : ~key[0];
+        prev_sa = k0 > 0 ? sa[k0 - 1] : IdxT(0);
+      }
+      if (lane == 31) next_key = k0 + 4 < count ? keys[k0 + 4] : ~key[3];
+    } else {  // the last row of the array
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint64_t k = k0 + j < count ? k0 + j : count - 1;
+        key[j] = keys[k];
+        s[j] = sa[k];
+      }
+      const uint64_t kp = k0 > 0 ? (k0 - 1 < count ? k0 - 1 : count - 1) : 0;
+      prev_key = k0 > 0 ? keys[kp] : ~key[0];
+      prev_sa = k0 > 0 ? sa[kp] : IdxT(0);
+      next_key = k0 + 4 < count ? keys[k0 + 4] : ~key[3];
+    }
+    unsigned nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint64_t pk = j ? key[j - 1] : prev_key;
+      const uint64_t ps = j ? s[j - 1] : prev_sa;
+      const uint64_t nk = j < 3 ? key[j + 1] : next_key;
+      const bool exists = k0 + j < end;
+      const bool eq_prev = pk == key[j];
+      // past the end of the array the clamped loads repeat the last element: not a neighbour
+      const bool eq_next = (nk == key[j]) & (k0 + j + 1 < count);
+      l[j] = eq_prev ? kLcpUnset<IdxT> : key_lcp_value<IdxT>(pk, key[j], ps, s[j], n, log2_bits);
+      nib |= (exists & (eq_prev | eq_next)) ? 1u << j : 0u;
+    }
+    if (wbase + 128 <= end) {
+      store4(lcp + k0, l);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k0 + j < end) lcp[k0 + j] = l[j];
+    }
+    tied_here += __popc(nib);
+    // 8 lanes x 4 flags = one 32-bit word of the bitmap
+    unsigned word = nib << (4u * (lane & 7u));
+    word |= __shfl_xor_sync(0xffffffffu, word, 1);
+    word |= __shfl_xor_sync(0xffffffffu, word, 2);
+    word |= __shfl_xor_sync(0xffffffffu, word, 4);
+    if ((lane & 7u) == 0 && k0 < end) tied_bits[k0 >> 5] = word;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) tied_here += __shfl_xor_sync(0xffffffffu, tied_here, d);
+  if (lane == 0) warp_sums[warp] = tied_here;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint64_t total = 0;
+#pragma unroll
+    for (int w = 0; w < kKeyLcpThreads / 32; ++w) total += warp_sums[w];
+    partial[blockIdx.x] = static_cast<IdxT>(total);
+  }
+}
 
 // The suffixes still being ordered, in SA order; the members of a group are consecutive.
 template <class IdxT>
@@ -518,6 +626,63 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const Idx
   }
 }
 
+// Mid groups of at most kWarpGroup suffixes — the bulk of them: a repeat family's 20-mer with one
+// substitution is shared by ~100 copies — are sorted by one warp each (eight groups per CTA at a
+// time, warp barriers only); the CTA-wide kernel above spends most of its threads and all of its
+// block barriers idling on groups this small.
+constexpr unsigned kWarpGroup = 128;
+
+template <class CompT, class IdxT>
+__global__ void __launch_bounds__(kGroupSortThreads) group_sort_warp_kernel(const IdxT* __restrict__ group_first,
+                                                                            const IdxT* __restrict__ group_size,
+                                                                            const unsigned long long* __restrict__ group_count,
+                                                                            const CompT* __restrict__ comp_in,
+                                                                            const IdxT* __restrict__ idx_in,
+                                                                            CompT* __restrict__ comp_out,
+                                                                            IdxT* __restrict__ idx_out) {
+  constexpr int kWarps = kGroupSortThreads / 32;
+  __shared__ CompT k_all[kWarps][kWarpGroup];
+  __shared__ IdxT v_all[kWarps][kWarpGroup];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  CompT* k = k_all[warp];
+  IdxT* v = v_all[warp];
+  const unsigned long long groups = *group_count;
+  for (unsigned long long grp = static_cast<unsigned long long>(blockIdx.x) * kWarps + warp; grp < groups;
+       grp += static_cast<unsigned long long>(gridDim.x) * kWarps) {
+    const uint64_t first = group_first[grp];
+    const unsigned size = static_cast<unsigned>(group_size[grp]);
+    const unsigned padded = size > 64 ? 128u : 64u;
+    for (unsigned e = lane; e < padded; e += 32) {
+      // padding sorts last: largest key and a suffix index no suffix has
+      k[e] = e < size ? comp_in[first + e] : ~CompT(0);
+      v[e] = e < size ? idx_in[first + e] : ~IdxT(0);
+    }
+    __syncwarp();
+    for (unsigned span = 2; span <= padded; span <<= 1) {
+      for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
+        for (unsigned pr = lane; pr < (padded >> 1); pr += 32) {
+          const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
+          const unsigned j = i | stride;
+          const bool up = (i & span) == 0;
+          const CompT a = k[i], b = k[j];
+          const IdxT va = v[i], vb = v[j];
+          const bool greater = a > b || (a == b && va > vb);  // (comp, suffix) pairs are distinct
+          if (greater == up) {
+            k[i] = b, k[j] = a;
+            v[i] = vb, v[j] = va;
+          }
+        }
+        __syncwarp();
+      }
+    }
+    for (unsigned e = lane; e < size; e += 32) {
+      comp_out[first + e] = k[e];
+      idx_out[first + e] = v[e];
+    }
+    __syncwarp();  // the staging area is refilled by the next group
+  }
+}
+
 // One refinement round on the active list.  comp_a[t] orders the members of a group: the low
 // second_bits bits are the second key (text beyond the current depth, or a rank); with
 // kGroupInComp the group head (plus one for suffixes that reach the current depth inside the
@@ -544,9 +709,10 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   trace_point(eng, "  round: comps built");
   DevBuf<uint8_t> big_flag(m, st);
   const uint64_t mid_capacity = m / (kSmallGroup + 1) + 1;
-  DevBuf<IdxT> mid_first(mid_capacity, st), mid_size(mid_capacity, st);
-  DevBuf<unsigned long long> mid_count(1, st);
-  CAPSB_CUDA(cudaMemsetAsync(mid_count.get(), 0, sizeof(unsigned long long), st));
+  DevBuf<IdxT> mid_first(mid_capacity, st), mid_size(mid_capacity, st);      // kWarpGroup < size <= kMidGroup
+  DevBuf<IdxT> warp_first(mid_capacity, st), warp_size(mid_capacity, st);    // kSmallGroup < size <= kWarpGroup
+  DevBuf<unsigned long long> mid_count(2, st);                               // [0] CTA-sorted, [1] warp-sorted
+  CAPSB_CUDA(cudaMemsetAsync(mid_count.get(), 0, 2 * sizeof(unsigned long long), st));
   {
     const CompT* c = comp_a.get();
     const IdxT* s = act.idx.get();
@@ -555,6 +721,8 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     uint8_t* big = big_flag.get();
     IdxT* mf = mid_first.get();
     IdxT* ms = mid_size.get();
+    IdxT* wf = warp_first.get();
+    IdxT* ws = warp_size.get();
     unsigned long long* mc = mid_count.get();
     launch_map(dev, st, m, [=] __device__(uint64_t t) {
       const IdxT grp = g[t];
@@ -575,9 +743,10 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
             else
               hi = mid;
           }
-          const unsigned long long slot = atomicAdd(mc, 1ull);
-          mf[slot] = static_cast<IdxT>(first);
-          ms[slot] = static_cast<IdxT>(hi - first);
+          const bool by_warp = hi - first <= kWarpGroup;
+          const unsigned long long slot = atomicAdd(mc + (by_warp ? 1 : 0), 1ull);
+          (by_warp ? wf : mf)[slot] = static_cast<IdxT>(first);
+          (by_warp ? ws : ms)[slot] = static_cast<IdxT>(hi - first);
         }
         return;
       }
@@ -602,6 +771,11 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
                                                                                    : static_cast<uint64_t>(dev.sm_count) * 8;
     CAPSB_LAUNCH((group_sort_kernel<CompT, IdxT>), static_cast<unsigned>(want), kGroupSortThreads, kSortSmem, st,
                  mid_first.get(), mid_size.get(), mid_count.get(), c, s, sorted_c, sorted_i);
+    const uint64_t warp_ctas = mid_capacity / (kGroupSortThreads / 32) + 1;
+    const uint64_t warp_grid = warp_ctas < static_cast<uint64_t>(dev.sm_count) * 16 ? warp_ctas
+                                                                                     : static_cast<uint64_t>(dev.sm_count) * 16;
+    CAPSB_LAUNCH((group_sort_warp_kernel<CompT, IdxT>), static_cast<unsigned>(warp_grid), kGroupSortThreads, 0, st,
+                 warp_first.get(), warp_size.get(), mid_count.get() + 1, c, s, sorted_c, sorted_i);
   }
   trace_point(eng, "  round: mid groups sorted");
   {
@@ -752,7 +926,32 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
   };
   ActiveList<IdxT> act;
-  act.m = scan_total<IdxT, OpSum>(eng, count, in_group);
+  DevBuf<uint32_t> tied_bits;
+  const bool vector_ok =
+      ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(d_sa) | reinterpret_cast<uintptr_t>(d_lcp)) & 15u) == 0;
+  if (vector_ok) {
+    // one streaming sweep: key-derived LCPs, tied bitmap, tied count per chunk (key_lcp_count_kernel)
+    ScanScratch<IdxT>& sc = eng.scan_scratch<IdxT>();
+    const Chunking ck = make_chunking(count, kScanTile, sc.max_blocks);
+    tied_bits.alloc(count / 32 + 8, st);
+    CAPSB_LAUNCH((key_lcp_count_kernel<IdxT>), ck.blocks, kKeyLcpThreads, 0, st, keys, d_sa, d_lcp, tied_bits.get(),
+                 count, ck.chunk, n, log2_bits, sc.partial.get());
+    CAPSB_LAUNCH((scan_spine_kernel<IdxT, OpSum>), 1, kScanThreads, 0, st, ck.blocks, sc.partial.get(), sc.total.get());
+    IdxT total;
+    read_back(st, &total, sc.total.get(), sizeof(IdxT));
+    act.m = total;
+  } else {  // caller arrays that are not 16-byte aligned: the same pass, element by element
+    auto in_group_and_lcp = [=] __device__(uint64_t k) -> IdxT {
+      const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
+      const uint64_t a = keys[kp], b = keys[k], c = keys[kn];
+      const IdxT sa_prev = d_sa[kp], sa_here = d_sa[k];
+      if (k > 0)
+        d_lcp[k] = a == b ? kLcpUnset<IdxT>  // until the pair-chain step or the deep-LCP stage
+                          : key_lcp_value<IdxT>(a, b, sa_prev, sa_here, n, log2_bits);
+      return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
+    };
+    act.m = scan_total<IdxT, OpSum>(eng, count, in_group_and_lcp);
+  }
   act.pos.alloc(act.m, st);
   act.idx.alloc(act.m, st);
   act.group.alloc(act.m, st);
@@ -763,24 +962,18 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     IdxT* p0 = tied.pos.get();
     IdxT* s = act.idx.get();
     IdxT* g = act.group.get();
-    select_finish<IdxT>(
-        eng, count, in_group,
-        [=] __device__(uint64_t k, IdxT slot) {
-          const uint64_t kp = k > 0 ? k - 1 : 0;
-          const uint64_t ka = keys[kp], kb = keys[k];
-          const IdxT sa_prev = d_sa[kp], sa_here = d_sa[k];
-          p[slot] = p0[slot] = static_cast<IdxT>(k);
-          s[slot] = sa_here;
-          if (k > 0)
-            d_lcp[k] = ka == kb ? kLcpUnset<IdxT>  // until the pair-chain step or the deep-LCP stage
-                                : key_lcp_value<IdxT>(ka, kb, sa_prev, sa_here, n, log2_bits);
-        },
-        [=] __device__(uint64_t k) {
-          const uint64_t kp = k > 0 ? k - 1 : 0;
-          const uint64_t ka = keys[kp], kb = keys[k];
-          const IdxT sa_prev = d_sa[kp], sa_here = d_sa[k];
-          if (k > 0) d_lcp[k] = key_lcp_value<IdxT>(ka, kb, sa_prev, sa_here, n, log2_bits);
-        });
+    auto collect = [=] __device__(uint64_t k, IdxT slot) {
+      p[slot] = p0[slot] = static_cast<IdxT>(k);
+      s[slot] = d_sa[k];
+    };
+    if (vector_ok) {
+      const uint32_t* bits = tied_bits.get();
+      select_finish<IdxT>(
+          eng, count, [=] __device__(uint64_t k) -> IdxT { return (bits[k >> 5] >> (k & 31u)) & 1u; }, collect);
+    } else {
+      select_finish<IdxT>(eng, count, in_group, collect);
+    }
+    tied_bits.release();
     // group head (global SA position) of every active suffix: running maximum of the heads
     scan_full<IdxT, OpMax, true>(
         eng, act.m,
@@ -1065,8 +1258,7 @@ void plcp_for_pairs(Engine& eng, const PackedText& pt, const IdxT* pos_i, PosJ p
     });
   }
   unsigned long long h_cnt[2];
-  CAPSB_CUDA(cudaMemcpyAsync(h_cnt, counters.get(), sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
-  CAPSB_CUDA(cudaStreamSynchronize(st));
+  read_back(st, h_cnt, counters.get(), sizeof(h_cnt));
   eng.stats.deep_lcp_direct += h_cnt[0];
   eng.stats.deep_lcp_long += h_cnt[1];
   if (h_cnt[1] > 0) {

@@ -28,6 +28,7 @@ Engine::Engine(int device) {
   ArenaScope scope(&arena);
   CAPSB_CUDA(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
   stream = own_stream;
+  CAPSB_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
   radix.init(dev, stream);
   scan32.init(dev, stream);
   scan64.init(dev, stream);
@@ -43,7 +44,26 @@ Engine::~Engine() {
   scan32 = ScanScratch<uint32_t>();
   scan64 = ScanScratch<uint64_t>();
   for (cudaEvent_t e : events) cudaEventDestroy(e);
+  if (copy_stream) cudaStreamDestroy(copy_stream);
   if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+void Engine::sa_is_final(const void* d_sa, uint64_t first, uint64_t count, size_t idx_bytes) {
+  if (!sa_sink || count == 0) return;
+  cudaEvent_t ready;
+  if (!events.empty()) {
+    ready = events.back();
+    events.pop_back();
+  } else {
+    CAPSB_CUDA(cudaEventCreate(&ready));
+  }
+  CAPSB_CUDA(cudaEventRecord(ready, stream));
+  CAPSB_CUDA(cudaStreamWaitEvent(copy_stream, ready, 0));
+  events.push_back(ready);  // the wait has captured this recording
+  if (sa_sink_started) CAPSB_CUDA(cudaEventRecord(sa_sink_started, copy_stream));
+  CAPSB_CUDA(cudaMemcpyAsync(static_cast<char*>(sa_sink) + first * idx_bytes, d_sa, count * idx_bytes,
+                             cudaMemcpyDeviceToHost, copy_stream));
+  sa_sunk = true;
 }
 
 template <class IdxT>
@@ -84,6 +104,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
     refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, n, 0, n, tied);
   }
+  eng.sa_is_final(d_sa, 0, n, sizeof(IdxT));
   first_position_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
   eng.stats.tied_after_key_sort = tied.m;
   clock.mark();  // 4

@@ -75,9 +75,7 @@ Route<IdxT> plan_route(Engine& eng, Comm& comm, uint64_t m, DestFn dest) {
     r.perm.alloc(m, st);
     DevBuf<uint8_t> sorted_dest(m, st);
     radix_pass<uint8_t, IdxT>(st, eng.radix, DestSource<IdxT, DestFn>{dest}, m, 0, sorted_dest.get(), r.perm.get());
-    CAPSB_CUDA(cudaMemcpyAsync(r.send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t),
-                               cudaMemcpyDeviceToHost, st));
-    CAPSB_CUDA(cudaStreamSynchronize(st));
+    read_back(st, r.send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t));
   }
   std::vector<uint64_t> matrix(static_cast<size_t>(world) * world);
   comm.all_gather_host(r.send_counts.data(), world * sizeof(uint64_t), matrix.data(), st);
@@ -526,6 +524,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, bucket_count, bucket_offset, n, tied);
   }
   eng.stats.tied_after_key_sort = tied.m;
+  eng.sa_is_final(d_sa, bucket_offset, bucket_count, sizeof(IdxT));
   clock.mark("ties resolved");  // 5
 
   // ---- LCP ----------------------------------------------------------------------------------
@@ -537,9 +536,8 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     } mine{bucket_count, 0, 0};
     if (bucket_count) {
       IdxT last_idx;
-      CAPSB_CUDA(cudaMemcpyAsync(&mine.last_key, keys + bucket_count - 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
-      CAPSB_CUDA(cudaMemcpyAsync(&last_idx, d_sa + bucket_count - 1, sizeof(IdxT), cudaMemcpyDeviceToHost, st));
-      CAPSB_CUDA(cudaStreamSynchronize(st));
+      read_back(st, &mine.last_key, keys + bucket_count - 1, sizeof(uint64_t));
+      read_back(st, &last_idx, d_sa + bucket_count - 1, sizeof(IdxT));
       mine.last_idx = last_idx;
     }
     std::vector<Edge> edges(world);
