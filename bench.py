@@ -43,6 +43,10 @@ WORKLOADS = {
                        desc="100 Mbp uniform random ACGT + newline mapped to C (config 2)"),
     "genome100m": dict(n=100_000_000, kind="genome_like", seed=3, desc="config 3 scaled to 100 Mbp"),
 }
+# DRAM traffic of the scatter kernel relative to its algorithmic bytes, from the committed
+# `ncu --set full` capture (profiles/r01/scatter_ncu_full_v4.csv: dram__bytes_read.sum 1.310726 GB +
+# dram__bytes_write.sum 1.234758 GB per launch over 100 000 001 (u64, u32) pairs = 24 B each)
+NCU_TRAFFIC_RATIO = (1.310726e9 + 1.234758e9) / (24.0 * 100_000_001)
 CPU_SAMPLE = 32_000_000   # prefix of the workload the CPU reference is timed on
 CPU_SUBPROBLEMS = 256      # the reference's best case in SURVEY.md §6 (default 8192 is ~2x slower)
 
@@ -278,7 +282,10 @@ def main():
     roofline = {
         "kernel": "radix_scatter_kernel", "bound": "hbm",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "peak_source": peak_kind, "traffic": None,
+        "peak_source": peak_kind,
+        "traffic": NCU_TRAFFIC_RATIO * scatter_bytes / max(1, scatter_launches),
+        "traffic_source": "ncu --set full capture of this kernel (profiles/r01/scatter_ncu_full_v4.csv): dram read + "
+                          f"write = {NCU_TRAFFIC_RATIO:.3f} x algorithmic bytes, scaled to this run's mean launch",
         "launches_timed": scatter_launches, "avg_launch_ms": scatter_ms / max(1, scatter_launches),
         "share_of_step": scatter_ms / args.steps / dev_ms,
         "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches),

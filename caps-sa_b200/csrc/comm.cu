@@ -201,19 +201,32 @@ NcclComm::~NcclComm() {
 void NcclComm::all_to_all_v(const void* send, const uint64_t* send_counts, void* recv, const uint64_t* recv_counts,
                             size_t elem_bytes, cudaStream_t st) {
   const NcclApi& api = nccl();
+  // the piece that stays on this rank is a plain device copy (through NCCL it would be a
+  // send/recv pair sharing the channels with the NVLink traffic)
+  {
+    uint64_t soff = 0, roff = 0;
+    for (int p = 0; p < rank; ++p) soff += send_counts[p], roff += recv_counts[p];
+    if (send_counts[rank] != recv_counts[rank]) fail("all_to_all_v: count mismatch");
+    if (send_counts[rank])
+      CAPSB_CUDA(cudaMemcpyAsync(static_cast<char*>(recv) + roff * elem_bytes,
+                                 static_cast<const char*>(send) + soff * elem_bytes, send_counts[rank] * elem_bytes,
+                                 cudaMemcpyDeviceToDevice, st));
+  }
   nccl_check(api.GroupStart(), "ncclGroupStart");
   uint64_t soff = 0, roff = 0;
   for (int p = 0; p < world; ++p) {
-    if (send_counts[p]) {
-      nccl_check(api.Send(static_cast<const char*>(send) + soff * elem_bytes, send_counts[p] * elem_bytes, kNcclUint8,
-                          p, comm_, st),
-                 "ncclSend");
-      if (p != rank) bytes_sent += send_counts[p] * elem_bytes;
+    if (p != rank) {
+      if (send_counts[p]) {
+        nccl_check(api.Send(static_cast<const char*>(send) + soff * elem_bytes, send_counts[p] * elem_bytes,
+                            kNcclUint8, p, comm_, st),
+                   "ncclSend");
+        bytes_sent += send_counts[p] * elem_bytes;
+      }
+      if (recv_counts[p])
+        nccl_check(api.Recv(static_cast<char*>(recv) + roff * elem_bytes, recv_counts[p] * elem_bytes, kNcclUint8, p,
+                            comm_, st),
+                   "ncclRecv");
     }
-    if (recv_counts[p])
-      nccl_check(api.Recv(static_cast<char*>(recv) + roff * elem_bytes, recv_counts[p] * elem_bytes, kNcclUint8, p,
-                          comm_, st),
-                 "ncclRecv");
     soff += send_counts[p];
     roff += recv_counts[p];
   }

@@ -42,6 +42,13 @@ void caps_port_map_acgt(char* text, uint64_t n);
 int caps_check_sa_lcp(const char* text, uint64_t n, const void* sa, const void* lcp,
                       int idx_bytes, uint64_t* bad_pos);
 
+/* The same validation for a text that is its first `period` (<= 4096) bytes repeated, with OpenMP
+ * loops and the LCP from the closed form for periodic texts (sa_check.c) — for the 1 Gbp
+ * periodic text of BASELINE config 4, where the sequential walk above takes minutes.
+ * Extra code: 5 = the text is not period-periodic. */
+int caps_check_sa_lcp_periodic(const char* text, uint64_t n, uint64_t period, const void* sa, const void* lcp,
+                               int idx_bytes, uint64_t* bad_pos);
+
 /* Naive O(n^2 log n) SA + direct LCP for tiny inputs (third, trivially-correct oracle;
  * same role as the reference's chatgpt_baseline.py:5-28). */
 int caps_naive_sa_lcp(const char* text, uint64_t n, uint64_t* sa_out, uint64_t* lcp_out);

@@ -74,6 +74,80 @@ done:
   return rc;
 }
 
+/* Validator for the 1 Gbp periodic text of BASELINE config 4(i), where the sequential Kasai
+ * walk above is too slow to run on a GPU box's host: text = its first `period` bytes repeated.
+ * Same predicates — permutation, suffix order through the inverse permutation — but OpenMP
+ * loops, and the LCP from the closed form for periodic texts: with L = n - max(a, b),
+ *   lcp(a, b) = L                           if a = b (mod period)
+ *             = min(L, mis[a % P][b % P])   otherwise, mis = first offset at which the two
+ *                                           rotations of the unit differ (computed by direct
+ *                                           comparison of the rotations).
+ * Returns the codes of caps_check_sa_lcp, 5 if the text is not period-periodic. */
+int caps_check_sa_lcp_periodic(const char* text, uint64_t n, uint64_t period, const void* sa, const void* lcp,
+                               int idx_bytes, uint64_t* bad_pos) {
+  if ((idx_bytes != 4 && idx_bytes != 8) || !text || !sa || !lcp || period == 0 || period > 4096) return 4;
+  if (n == 0) return 0;
+  const signed char* t = (const signed char*)text;
+  const uint64_t P = period;
+  int rc = 0;
+  uint64_t bad = UINT64_MAX;
+#define CAPS_FAIL(code, where)                        \
+  do {                                                \
+    _Pragma("omp critical(caps_check_fail)") {        \
+      if ((where) < bad) rc = (code), bad = (where);  \
+    }                                                 \
+  } while (0)
+
+  int periodic = 1;
+#pragma omp parallel for schedule(static) reduction(&& : periodic)
+  for (uint64_t i = P; i < n; ++i) periodic = periodic && t[i] == t[i - P];
+  if (!periodic) return 5;
+
+  uint32_t* mis = malloc(P * P * sizeof(uint32_t));
+  uint64_t* rank = malloc((n + 1) * sizeof(uint64_t));
+  unsigned char* seen = calloc(n, 1);
+  if (!mis || !rank || !seen) {
+    free(mis), free(rank), free(seen);
+    return 4;
+  }
+#pragma omp parallel for schedule(dynamic, 8)
+  for (uint64_t r = 0; r < P; ++r)
+    for (uint64_t q = 0; q < P; ++q) {
+      uint64_t m = 0;
+      while (m < P && t[(r + m) % P] == t[(q + m) % P]) ++m;
+      mis[r * P + q] = m < P ? (uint32_t)m : UINT32_MAX; /* equal rotations: unit not primitive */
+    }
+
+#pragma omp parallel for schedule(static)
+  for (uint64_t k = 0; k < n; ++k) { /* permutation of [0, n) */
+    const uint64_t s = get_idx(sa, idx_bytes, k);
+    if (s >= n || __atomic_exchange_n(&seen[s], 1, __ATOMIC_RELAXED)) {
+      CAPS_FAIL(1, k);
+    } else {
+      rank[s] = k + 1;
+    }
+  }
+  rank[n] = 0; /* the empty suffix precedes everything */
+  if (rc) goto done;
+
+#pragma omp parallel for schedule(static)
+  for (uint64_t k = 1; k < n; ++k) {
+    const uint64_t a = get_idx(sa, idx_bytes, k - 1), b = get_idx(sa, idx_bytes, k);
+    if (t[a] > t[b] || (t[a] == t[b] && rank[a + 1] >= rank[b + 1])) CAPS_FAIL(2, k);
+    const uint64_t L = n - (a > b ? a : b);
+    const uint64_t m = a % P == b % P ? UINT64_MAX : mis[(a % P) * P + b % P];
+    const uint64_t want = m == UINT32_MAX || m > L ? L : m;
+    if (get_idx(lcp, idx_bytes, k) != want) CAPS_FAIL(3, k);
+  }
+  if (get_idx(lcp, idx_bytes, 0) != 0) CAPS_FAIL(3, 0);
+
+done:
+#undef CAPS_FAIL
+  if (rc && bad_pos) *bad_pos = bad;
+  free(mis), free(rank), free(seen);
+  return rc;
+}
+
 typedef struct {
   const signed char* t;
   uint64_t n;

@@ -13,6 +13,7 @@
 #include <iostream>
 #include <limits>
 #include <string>
+#include <vector>
 
 
 namespace
@@ -56,12 +57,29 @@ void read_input(const std::string& path, Pinned_Text& text)
 }
 
 
+// Text form of the result: the suffix array on one line, the LCP array on the next, entries
+// separated by blanks (the reference declares this as `pretty_print`, src/main.cpp:31-40, and
+// lists `--pretty-print` in its usage line, :49, but never parses the flag; here it is live).
 template <typename idx_t>
-void build_and_dump(const Pinned_Text& text, const std::size_t subproblems, const std::size_t context, std::ofstream& output)
+void pretty_print(const CaPS_SA::Suffix_Array<idx_t>& suf_arr, std::ofstream& output)
+{
+    const std::size_t n = suf_arr.n();
+    for(std::size_t i = 0; i < n; ++i)
+        output << suf_arr.SA()[i] << " \n"[i == n - 1];
+    for(std::size_t i = 0; i < n; ++i)
+        output << suf_arr.LCP()[i] << " \n"[i == n - 1];
+}
+
+
+template <typename idx_t>
+void build_and_dump(const Pinned_Text& text, const std::size_t subproblems, const std::size_t context, const bool pretty, std::ofstream& output)
 {
     CaPS_SA::Suffix_Array<idx_t> suf_arr(text.data, static_cast<idx_t>(text.size), static_cast<idx_t>(subproblems), static_cast<idx_t>(context));
     suf_arr.construct();
-    suf_arr.dump(output);
+    if(pretty)
+        pretty_print(suf_arr, output);
+    else
+        suf_arr.dump(output);
 }
 
 }
@@ -75,10 +93,20 @@ int main(int argc, char* argv[])
         return EXIT_FAILURE;
     }
 
-    const std::string ip_path(argv[1]);
-    const std::string op_path(argv[2]);
-    const std::size_t subproblem_count(argc >= 4 ? std::atoi(argv[3]) : 0);
-    const std::size_t max_context(argc >= 5 ? std::atoi(argv[4]) : 0);
+    // `--pretty-print` may stand anywhere after the two paths; the other arguments keep the
+    // reference's positions.
+    bool pretty = false;
+    std::vector<const char*> args;
+    for(int i = 0; i < argc; ++i)
+        if(i >= 3 && std::string(argv[i]) == "--pretty-print")
+            pretty = true;
+        else
+            args.push_back(argv[i]);
+
+    const std::string ip_path(args[1]);
+    const std::string op_path(args[2]);
+    const std::size_t subproblem_count(args.size() >= 4 ? std::atoi(args[3]) : 0);
+    const std::size_t max_context(args.size() >= 5 ? std::atoi(args[4]) : 0);
 
     caps_sa_gpu_engine* const engine = caps_sa_gpu_engine_create(std::getenv("CAPS_SA_DEVICE") ? std::atoi(std::getenv("CAPS_SA_DEVICE")) : 0);
     if(!engine)
@@ -103,9 +131,9 @@ int main(int argc, char* argv[])
     const std::size_t n = text.size;
     std::cerr << "Text length: " << n << ".\n";
     if(n <= std::numeric_limits<uint32_t>::max())
-        build_and_dump<uint32_t>(text, subproblem_count, max_context, output);
+        build_and_dump<uint32_t>(text, subproblem_count, max_context, pretty, output);
     else
-        build_and_dump<uint64_t>(text, subproblem_count, max_context, output);
+        build_and_dump<uint64_t>(text, subproblem_count, max_context, pretty, output);
 
     output.close();
 

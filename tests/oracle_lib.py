@@ -48,6 +48,8 @@ def port():
         lib.caps_port_map_acgt.restype = None
         lib.caps_check_sa_lcp.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp.restype = C.c_int
+        lib.caps_check_sa_lcp_periodic.argtypes = [p, u64, u64, p, p, C.c_int, C.POINTER(u64)]
+        lib.caps_check_sa_lcp_periodic.restype = C.c_int
         lib.caps_naive_sa_lcp.argtypes = [p, u64, p, p]
         lib.caps_naive_sa_lcp.restype = C.c_int
         _port = lib
@@ -122,6 +124,19 @@ def check_sa_lcp(text, sa: np.ndarray, lcp: np.ndarray):
     bad = C.c_uint64(0)
     rc = port().caps_check_sa_lcp(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
                                   sa.dtype.itemsize, C.byref(bad))
+    return rc, bad.value
+
+
+def check_sa_lcp_periodic(text, period: int, sa: np.ndarray, lcp: np.ndarray):
+    """check_sa_lcp for a text that is its first `period` bytes repeated: multi-threaded, LCP from
+    the closed form for periodic texts (oracle/sa_check.c)."""
+    t = _as_text(text)
+    sa = np.ascontiguousarray(sa)
+    lcp = np.ascontiguousarray(lcp)
+    assert sa.dtype == lcp.dtype and sa.dtype in (np.uint32, np.uint64)
+    bad = C.c_uint64(0)
+    rc = port().caps_check_sa_lcp_periodic(t.ctypes.data, len(t), period, sa.ctypes.data, lcp.ctypes.data,
+                                           sa.dtype.itemsize, C.byref(bad))
     return rc, bad.value
 
 

@@ -224,6 +224,24 @@ def test_cli_dump_matches_reference_cli(pkg, synth, tmp_path):
         assert out_gpu.read_bytes() == oracle_lib.dump_bytes(len(mapped), sa, lcp)
 
 
+def test_cli_pretty_print(pkg, synth, tmp_path):
+    """`--pretty-print` (reference usage line, src/main.cpp:49; format of its pretty_print, :31-40):
+    SA on the first line, LCP on the second, blank-separated."""
+    raw = synth.ecoli_like_fasta(seed=5, bases=20_000)
+    src = tmp_path / "small.fa"
+    raw.tofile(src)
+    out = tmp_path / "pretty.txt"
+    proc = subprocess.run([os.path.join(ROOT, "bin", "caps_sa"), str(src), str(out), "16", "0", "--pretty-print"],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    lines = out.read_text().split("\n")
+    assert len(lines) == 3 and lines[2] == ""
+    mapped = synth.map_acgt(raw)
+    sa, lcp = oracle_lib.port_sa_lcp(mapped, subproblems=16)
+    assert np.array_equal(np.array(lines[0].split(), dtype=np.uint64), sa.astype(np.uint64))
+    assert np.array_equal(np.array(lines[1].split(), dtype=np.uint64), lcp.astype(np.uint64))
+
+
 def test_map_acgt_kernel(engine, synth):
     raw = np.concatenate([np.arange(256, dtype=np.uint8).repeat(5), synth.random_bytes(100_001, 9)])
     got = raw.copy()
