@@ -62,6 +62,23 @@ struct EventPair {
   }
 };
 
+// Bounded context (reference ctor argument 4, src/Suffix_Array.cpp:25).  The
+// reference then compares suffixes on their first max_context + 1 symbols only (:72-77): its SA
+// is sorted on that prefix with an order inside ties that depends on the subproblem count, and
+// its LCP entries are min(lcp, max_context) (except at its p - 1 partition boundaries, which it
+// patches with an unbounded compare, :440).  Here the construction is always exact — the exact
+// order is one of the orders the bounded comparison allows — and the LCP array is clamped, so
+// the documented properties hold for every subproblem count ("parity modulo ties").
+template <class IdxT>
+void clamp_lcp(Engine& eng, IdxT* d_lcp, uint64_t count, uint64_t max_context, uint64_t n) {
+  if (max_context == 0 || max_context >= n || count == 0) return;
+  const IdxT cap = static_cast<IdxT>(max_context);
+  capsb::launch_map(eng.dev, eng.stream, count, [=] __device__(uint64_t k) {
+    const IdxT v = d_lcp[k];
+    if (v > cap) d_lcp[k] = cap;
+  });
+}
+
 // Host-buffer entry points: while in scope, the engine copies the suffix array to `sa_out` as
 // soon as it is final (Engine::sa_is_final); finish() copies the rest once the construction is
 // done.  All copies run on the engine's copy stream.
@@ -107,10 +124,6 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
   if (!engine) return bad_args("engine is NULL");
   if (n > 0 && (!text || !sa_out || !lcp_out)) return bad_args("NULL buffer");
   if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
-  if (max_context != 0 && max_context < n) {
-    g_last_error = "bounded context (max_context < n) is not supported by the GPU engine";
-    return CAPS_SA_GPU_ERR_UNSUPPORTED;
-  }
   return guarded([&]() -> int {
     Engine& eng = engine->impl;
     capsb::ArenaScope arena_scope(&eng.arena);
@@ -125,6 +138,7 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
     CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
     CAPSB_CUDA(cudaEventRecord(h2d.b, st));
     capsb::build_sa_lcp<IdxT>(eng, d_text.get(), n, d_sa.get(), d_lcp.get());
+    clamp_lcp<IdxT>(eng, d_lcp.get(), n, max_context, n);
     results.finish(d_sa.get(), d_lcp.get(), sa_out, lcp_out, 0, n);
     eng.stats.ms_h2d = h2d.ms();
     return CAPS_SA_GPU_OK;
@@ -177,13 +191,6 @@ capsb::ShardResult<uint32_t>& shard_of<uint32_t>(Engine& eng) { return eng.shard
 template <>
 capsb::ShardResult<uint64_t>& shard_of<uint64_t>(Engine& eng) { return eng.shard64; }
 
-int check_context(uint64_t max_context, uint64_t n) {
-  if (max_context != 0 && max_context < n) {
-    g_last_error = "bounded context (max_context < n) is not supported by the GPU engine";
-    return CAPS_SA_GPU_ERR_UNSUPPORTED;
-  }
-  return CAPS_SA_GPU_OK;
-}
 
 // Text staging of the sharded construction from a host buffer: every rank uploads only its own
 // 1/world of the text over its own PCIe link and the ranks all-gather the pieces over NVLink
@@ -217,7 +224,6 @@ int construct_multi(const int* devices, int num_ranks, const char* text, uint64_
   if (!devices || num_ranks < 1 || num_ranks > 64) return bad_args("bad device list");
   if (n > 0 && (!text || !sa_out || !lcp_out)) return bad_args("NULL buffer");
   if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) return bad_args("n does not fit 32-bit indices");
-  if (const int rc = check_context(max_context, n)) return rc;
   return guarded([&]() -> int {
     int visible = 0;
     CAPSB_CUDA(cudaGetDeviceCount(&visible));
@@ -242,6 +248,7 @@ int construct_multi(const int* devices, int num_ranks, const char* text, uint64_
               capsb::build_sa_lcp_sharded<IdxT>(eng, comm, staged.buf.get(), n, shard);
               eng.stats.ms_h2d = staged.ms_h2d;
             }
+            clamp_lcp<IdxT>(eng, shard.lcp.get(), shard.count, max_context, n);
             results.finish(shard.sa.get(), shard.lcp.get(), sa_out, lcp_out, shard.offset, shard.count);
           }
           stats[r] = eng.stats;

@@ -31,7 +31,8 @@ public:
     typedef T_idx_ idx_t;
 
     // `T` must outlive the object.  `subproblem_count` is accepted for compatibility and used
-    // only as a tuning hint (the output never depended on it); `max_context` must be 0 or >= n.
+    // only as a tuning hint (the output never depended on it); with a bounded `max_context` the
+    // suffix array stays exact and LCP entries are capped at `max_context` (caps_sa_gpu.h).
     Suffix_Array(const char* T, idx_t n, idx_t subproblem_count = 0, idx_t max_context = 0);
 
     Suffix_Array(const Suffix_Array&) = delete;

@@ -28,7 +28,7 @@ extern "C" {
 #define CAPS_SA_GPU_OK 0
 #define CAPS_SA_GPU_ERR_ARGS 1     /* bad arguments (NULL pointers, n too large for the index width) */
 #define CAPS_SA_GPU_ERR_CUDA 2     /* CUDA / NCCL failure, including out of device memory */
-#define CAPS_SA_GPU_ERR_UNSUPPORTED 3 /* e.g. bounded context */
+#define CAPS_SA_GPU_ERR_UNSUPPORTED 3 /* reserved; nothing returns it at present */
 
 /* Opaque per-device engine: stream, scratch pools, statistics. */
 typedef struct caps_sa_gpu_engine caps_sa_gpu_engine;
@@ -85,8 +85,13 @@ int caps_sa_gpu_engine_set_kernel_timing(caps_sa_gpu_engine* engine, int enabled
  * Replaces the reference's construct() (src/Suffix_Array.cpp:466-494).  `text` is borrowed
  * host memory of n bytes; sa_out / lcp_out are caller-owned host arrays of n entries
  * (pinned memory from caps_sa_gpu_host_alloc makes the copies run at PCIe speed).
- * Blocking.  max_context: 0 or >= n only (the reference's default); otherwise
- * CAPS_SA_GPU_ERR_UNSUPPORTED.  num_gpus: 0 or 1 = one device (the engine's). */
+ * Blocking.  max_context: 0 or >= n = the reference's default (unbounded).  A bounded context
+ * (reference ctor argument 4, src/Suffix_Array.cpp:25,72-77) is implementation-defined in the
+ * reference — the order inside groups of suffixes that agree on their first max_context + 1
+ * symbols depends on its subproblem count.  Here the suffix array is always the exact one
+ * (one of the orders the bounded comparison allows) and the LCP entries are
+ * min(lcp, max_context), the reference's values everywhere except at its p - 1 partition
+ * boundaries (:440).  subproblem_count is accepted for compatibility and ignored. */
 int caps_sa_gpu_construct_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n,
                               uint32_t* sa_out, uint32_t* lcp_out, uint64_t subproblem_count,
                               uint64_t max_context);

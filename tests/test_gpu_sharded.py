@@ -64,6 +64,18 @@ def test_sharded_matches_oracle(pkg, synth, case, ranks):
     assert np.array_equal(obj.LCP(), want_lcp), f"LCP differs ({stats})"
 
 
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_sharded_bounded_context_caps_lcp(pkg, synth, ranks):
+    """Bounded context through the sharded entry point: exact SA, LCP capped (see
+    tests/test_gpu_parity.py: test_bounded_context for the comparison with the reference)."""
+    text, want_sa, want_lcp = oracle("genome_like_2M", synth)
+    sa = np.empty(len(text), dtype=np.uint32)
+    lcp = np.empty(len(text), dtype=np.uint32)
+    pkg.construct_multi(text, sa, lcp, device_list(pkg, ranks), subproblem_count=16, max_context=12)
+    assert np.array_equal(sa, want_sa)
+    assert np.array_equal(lcp, np.minimum(want_lcp, 12))
+
+
 @pytest.mark.parametrize("ranks", [2, 5])
 @pytest.mark.parametrize("case", ["acgt_odd_77777", "fibonacci_200k", "bytes256_300k"])
 def test_sharded_u64_indices(pkg, synth, case, ranks):

@@ -27,8 +27,8 @@ PY
   "$GPU" "$tmp/in.txt" "$tmp/gpu.bin" "$P" 2> "$tmp/gpu.err"; t2=$(date +%s.%N)
   if cmp -s "$tmp/ref.bin" "$tmp/gpu.bin"; then result="\033[32mcorrect\033[0m"; else result="\033[31mincorrect\033[0m"; status=1; fi
   echo "Random seed: $seed"
-  echo "True program runtime: $(echo "$t1 - $t0" | bc) seconds"
-  echo "Test program runtime: $(echo "$t2 - $t1" | bc) seconds"
+  echo "True program runtime: $(awk "BEGIN{printf \"%.3f\", $t1 - $t0}") seconds"
+  echo "Test program runtime: $(awk "BEGIN{printf \"%.3f\", $t2 - $t1}") seconds"
   echo -e "Output correctness: $result"
   rm -rf "$tmp"
 done
