@@ -690,9 +690,26 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_warp_kernel(cons
 // carry no group and only the large-group sort prepends it.  Orders every group, writes the new
 // order to d_sa, publishes the new group heads (when the refinement keeps ranks) and drops the
 // suffixes that are now alone in their group.
+//
+// Text rounds (comps = flag bit . next 63 bits of packed text, see refine_tied_groups) also settle
+// LCPs: where two neighbours of one group part ways in this round, their common prefix is the
+// depth the group agreed on plus the common leading symbols of their comps — the same
+// clz-of-XOR rule that gives the key-derived LCPs, one round deeper — so the entry is written here
+// and the pair never reaches the deep-LCP stage.  The value does not depend on which members end
+// up at the edges of the two new groups; only its bound by the shorter suffix does, and
+// refine_tied_groups applies that bound to every tied position once the order is final.
+template <class IdxT>
+struct TextRoundLcp {
+  IdxT* d_lcp = nullptr;  // null: not a text round
+  uint64_t depth = 0;     // symbols every member of a group agrees on before this round
+  uint64_t n = 0;
+  unsigned log2_bits = 0;
+};
+
 template <class IdxT, class CompT, bool kGroupInComp, class Ranks>
 void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_base, DevBuf<CompT> comp_a,
-                  unsigned second_bits, unsigned rank_bits, Ranks* publish_to) {
+                  unsigned second_bits, unsigned rank_bits, Ranks* publish_to,
+                  TextRoundLcp<IdxT> text_lcp = TextRoundLcp<IdxT>()) {
   using Wide = unsigned __int128;
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
@@ -857,8 +874,30 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     const IdxT* p = act.pos.get();
     IdxT* ng = new_group.get();
     launch_map(dev, st, m, [=] __device__(uint64_t t) {
-      d_sa[p[t]] = sorted_idx[t];
+      const IdxT here = sorted_idx[t];
+      d_sa[p[t]] = here;
       ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
+      // (captured outside the constexpr-if: an extended lambda may not first-capture inside one)
+      const TextRoundLcp<IdxT> tl = text_lcp;
+      const IdxT* og = old_group;
+      const CompT* sc = sorted_comp;
+      if constexpr (!kGroupInComp && sizeof(CompT) == 8) {
+        if (tl.d_lcp != nullptr && t > 0 && og[t] == og[t - 1]) {
+          const uint64_t ca = static_cast<uint64_t>(sc[t - 1]), cb = static_cast<uint64_t>(sc[t]);
+          if (ca != cb) {
+            uint64_t l;
+            if ((ca & cb) >> 63) {  // both suffixes reach the depth: compare the 63 text bits
+              const uint64_t x = (ca ^ cb) << 1;
+              l = tl.depth + (static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> tl.log2_bits);
+            } else {  // one of them ends before the depth: it is a prefix of its neighbour
+              const uint64_t a = sorted_idx[t - 1], b = here;
+              l = tl.n - (a > b ? a : b);
+            }
+            tl.d_lcp[p[t]] = static_cast<IdxT>(l);
+          }
+        }
+      }
+      (void)tl, (void)og, (void)sc;
     });
   }
   trace_point(eng, "  round: heads + sa written");
@@ -1042,7 +1081,8 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
         const uint64_t ih = i + depth;
         c[t] = ih < n ? (1ull << 63) | (text.window(ih) >> 1) : (n - 1 - i);
       });
-      refine_round<IdxT, uint64_t, false, Ranks>(eng, act, d_sa, pos_base, std::move(comp), 64, rank_bits, nullptr);
+      refine_round<IdxT, uint64_t, false, Ranks>(eng, act, d_sa, pos_base, std::move(comp), 64, rank_bits, nullptr,
+                                                 TextRoundLcp<IdxT>{d_lcp, h, n, log2_bits});
       h += text_step;
       total_active = ranks.global_sum(act.m);
       lap("text round", before);
@@ -1094,8 +1134,16 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     const IdxT* p0 = tied.pos.get();
     launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
       const uint64_t k = p0[t];
-      if (k > 0 && keys[k] != keys[k - 1])
-        d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+      if (k > 0) {
+        if (keys[k] != keys[k - 1]) {
+          d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+        } else {  // inside a key group: a text round's entry is still to be bounded by the shorter suffix
+          const IdxT v = d_lcp[k];
+          const uint64_t a = d_sa[k - 1], b = d_sa[k];
+          const uint64_t shorter = n - (a > b ? a : b);
+          if (v != kLcpUnset<IdxT> && static_cast<uint64_t>(v) > shorter) d_lcp[k] = static_cast<IdxT>(shorter);
+        }
+      }
       if (k + 1 < count && keys[k + 1] != keys[k])
         d_lcp[k + 1] = key_lcp_value<IdxT>(keys[k], keys[k + 1], d_sa[k], d_sa[k + 1], n, log2_bits);
     });
