@@ -198,7 +198,7 @@ def main():
     pkg = graft.load_package()
     if world > 1:
         from caps_sa_b200 import multi_gpu  # sharded path (torch.distributed plumbing + our kernels)
-        multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks)
+        multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks, NCU_TRAFFIC_RATIO)
         dist.barrier()
         dist.destroy_process_group()
         return

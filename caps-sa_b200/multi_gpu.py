@@ -150,7 +150,7 @@ def bind_to_gpu_cpus(device_index: int):
 
 
 # ---- bench.py, N > 1 -----------------------------------------------------------------------
-def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks):
+def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, traffic_ratio=None):
     """bench.py's multi-rank arm: same JSON contract, time = max over ranks, value = n / time.
     The text is fixed (strong scaling): every rank generates the same synthetic text."""
     rank = dist.get_rank()
@@ -288,7 +288,10 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks):
         "stage_ms_rank0": {k: round(v, 3) for k, v in stage_ms.items()},
         "roofline": {"kernel": "radix_scatter_kernel (rank 0)", "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_kind,
-                     "traffic": None, "launches_timed": scatter_launches,
+                     "traffic": (traffic_ratio * scatter_bytes / max(1, scatter_launches)) if traffic_ratio else None,
+                     "traffic_source": "ncu --set full capture of this kernel on one GPU (profiles/r01/scatter_ncu_full_v4.csv), "
+                                       "scaled to this run's mean launch",
+                     "launches_timed": scatter_launches,
                      "avg_launch_ms": scatter_ms / max(1, scatter_launches),
                      "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches)},
         "cpu_baseline": None, "clocks": clocks,
