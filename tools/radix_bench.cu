@@ -68,6 +68,34 @@ int main(int argc, char** argv) {
              (bytes + 8.0 * n) / (ms / reps) / 1e6, scatter_ms / launches, bytes / (scatter_ms / launches) / 1e6,
              bytes / (scatter_ms / launches) / 1e6 / 6546.0);
     }
+    // (u32 key, u32 value) records through the product layout: what a pass would cost if the four
+    // upper passes of the suffix sort carried a 32-bit high key
+    if (argc <= 4) {
+      DevBuf<uint32_t> k32a(n, st), k32b(n + (8u << 20), st);
+      {
+        uint32_t* d = k32a.get();
+        const uint64_t* src = ka.get();
+        launch_map(dev, st, n, [=] __device__(uint64_t i) { d[i] = static_cast<uint32_t>(src[i] >> 32); });
+      }
+      rs.variant = 0;
+      for (int w = 0; w < 3; ++w)
+        radix_pass<uint32_t, uint32_t>(st, rs, ArraySource<uint32_t, uint32_t>{k32a.get(), va.get()}, n, shift, k32b.get(),
+                                       vb.get());
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      rs.timer.reset();
+      for (int r = 0; r < reps; ++r)
+        radix_pass<uint32_t, uint32_t>(st, rs, ArraySource<uint32_t, uint32_t>{k32a.get(), va.get()}, n, shift, k32b.get(),
+                                       vb.get());
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      uint32_t launches = 0;
+      const float scatter_ms = rs.timer.drain(&launches);
+      printf("n=%llu (u32,u32) records, product layout: scatter %.4f ms (%.1f GB/s of 16 B/element)\n",
+             (unsigned long long)n, scatter_ms / launches, 16.0 * n / (scatter_ms / launches) / 1e6);
+      // leave the (u64,u32) output of the last variant in kb/vb for the check below
+      rs.variant = 5;
+      radix_pass<uint64_t, uint32_t>(st, rs, ArraySource<uint64_t, uint32_t>{ka.get(), va.get()}, n, shift, kb.get(), vb.get());
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+    }
     // correctness of the last variant run: output sorted by the digit, stable
     {
       std::vector<uint64_t> hk(1 << 20);
