@@ -286,12 +286,6 @@ struct LocalRanks {
   }
 };
 
-// ---------------------------------------------------------------------------------------
-// Prefix-doubling refinement.  d_sa[0..count) holds suffixes in key order (SA positions
-// pos_base .. pos_base + count of the final array); keys[] are their (masked) keys, which
-// order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
-// keys must be complete inside [0, count).
-// ---------------------------------------------------------------------------------------
 // LCP of two suffixes a, b (text positions) whose keys differ: clz(key_a ^ key_b) / bits, bounded
 // by the shorter suffix (zero padding can agree with real code-0 symbols past the end).
 template <class IdxT>
@@ -932,17 +926,20 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
 }
 
 // ---------------------------------------------------------------------------------------
-// Prefix-doubling refinement.  d_sa[0..count) holds suffixes in key order (SA positions
-// pos_base .. pos_base + count of the final array); keys[] are their (masked) keys, which
-// order them by their first h0 symbols.  On return d_sa is in suffix order.  Groups of equal
-// keys must be complete inside [0, count).
+// Refinement of the ties the key sort leaves.  d_sa[0..count) holds suffixes in key order (SA
+// positions pos_base .. pos_base + count of the final array); keys[] are their (masked) keys,
+// which order them by their first h0 symbols.  Groups of equal keys must be complete inside
+// [0, count).  On return d_sa is in suffix order, d_lcp holds every entry except those of
+// neighbours that stayed tied into the rank rounds (kLcpUnset: the permuted-LCP stage of the
+// caller, collect_deep_pairs + plcp_for_pairs), and `tied` lists the positions that were tied.
 //
-// Round 1 needs no rank array at all: the rank of suffix i + h0 after the key sort is a
-// monotone function of its key (equal exactly when the keys are equal), so the members of a
-// group are ordered by the key of their suffix i + h0, read straight from the packed text —
-// no lookups, and in the sharded path no exchange.  From round 2 on the second field is the
-// rank of suffix i + h, kept by the Ranks policy; it only ever stores ranks of suffixes that
-// have been tied (everything else is implicit, see LocalRanks / ShardedRanks).
+//   first pass   key-derived LCPs, bitmap and list of the tied positions (key_lcp_count_kernel);
+//   pair chains  groups of two are finished by one comparison per chain (resolve_pairs);
+//   text rounds  groups ordered by the next 63 bits of text: no rank array, no lookups, in the
+//                sharded path no exchange; the LCPs of the neighbours they separate fall out;
+//   rank rounds  prefix doubling on ranks kept by the Ranks policy, which only ever stores ranks
+//                of suffixes that have been tied (the rest is implicit, LocalRanks / ShardedRanks);
+//   last pass    LCPs at the edges of the key groups, bound by the shorter suffix inside them.
 // ---------------------------------------------------------------------------------------
 template <class IdxT, class Ranks>
 void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
@@ -957,7 +954,7 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
   // The suffixes still to be ordered: members of key groups with at least two suffixes.  The same
   // pass writes every LCP that the keys alone decide (neighbours with different keys) and marks
   // the rest unset; entries next to a tied group are provisional (their bound depends on which
-  // member ends up at the group's edge) and are rewritten by fix_group_edge_lcp afterwards.
+  // member ends up at the group's edge) and are rewritten by the last pass of this function.
   // (all loads unconditional, on clamped indices: a short-circuit would chain their latencies)
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
     const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
