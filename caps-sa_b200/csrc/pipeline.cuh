@@ -3,11 +3,13 @@
 //   sort_suffix_slice   stable LSD radix sort of a slice of suffixes on their packed-prefix key
 //                       (replaces permute + sort_subarrays/merge_sort, reference
 //                       src/Suffix_Array.cpp:112-184);
-//   refine_tied_groups  prefix-doubling rank refinement restricted to the suffixes that are
-//                       still tied (replaces the character compares inside merge, :69-80);
+//   refine_tied_groups  refinement restricted to the suffixes that are still tied — pair chains,
+//                       text rounds, then prefix doubling on ranks (replaces the character
+//                       compares inside merge, :69-80);
 //                       where the ranks live is a policy: one array (LocalRanks) or sharded by
 //                       text position with an exchange per round (ShardedRanks);
-//   key_lcp             LCP of neighbours with different keys: clz(key_a ^ key_b);
+//   key_lcp_count_kernel  first pass over the sorted keys: LCP of neighbours with different keys
+//                       (clz(key_a ^ key_b)), bitmap and counts of the tied positions;
 //   plcp_for_pairs      LCP of tied neighbours by the permuted-LCP recurrence
 //                       PLCP[i] = PLCP[i-1] - 1 on reducible positions and a packed-word
 //                       comparison on the irreducible ones (replaces the LCPs carried
@@ -1184,36 +1186,6 @@ uint64_t collect_deep_pairs(Engine& eng, const TiedSet<IdxT>& tied, const uint64
     pk[slot] = static_cast<IdxT>(k);
   });
   return m;
-}
-
-// ---------------------------------------------------------------------------------------
-// LCP of neighbours with different keys comes from the keys alone: clz(key_a ^ key_b) / bits,
-// bounded by the shorter suffix.  It needs the FINAL predecessor (the bound depends on which
-// member of the previous group ends up last), so it runs after the refinement.  The
-// predecessor of local position 0 is (prev_key, prev_idx) when has_prev, else LCP is 0.
-// ---------------------------------------------------------------------------------------
-template <class IdxT>
-void key_lcp(Engine& eng, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t n,
-             unsigned log2_bits, bool has_prev, uint64_t prev_key, uint64_t prev_idx) {
-  launch_map(eng.dev, eng.stream, count, [=] __device__(uint64_t k) {
-    uint64_t pk, a;
-    if (k == 0) {
-      if (!has_prev) {
-        d_lcp[0] = 0;
-        return;
-      }
-      pk = prev_key, a = prev_idx;
-    } else {
-      pk = keys[k - 1], a = d_sa[k - 1];
-    }
-    const uint64_t x = keys[k] ^ pk;
-    if (x != 0) {
-      const uint64_t b = d_sa[k];
-      const uint64_t shorter = n - (a > b ? a : b);
-      const uint64_t l = static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> log2_bits;
-      d_lcp[k] = static_cast<IdxT>(l < shorter ? l : shorter);
-    }
-  });
 }
 
 // Block-wide comparison for the few very long common prefixes (one CTA per pair).
