@@ -40,7 +40,7 @@ typedef struct caps_sa_gpu_stats {
   uint32_t idx_bytes;
   uint32_t bits_per_symbol;     /* 1, 2, 4 or 8: width of the packed codes */
   uint32_t alphabet_size;
-  uint32_t refine_rounds;       /* prefix-doubling rounds run on the tied suffixes */
+  uint32_t refine_rounds;       /* text and rank (prefix-doubling) rounds run on the tied suffixes */
   uint64_t tied_after_key_sort; /* suffixes whose sort key is shared with another suffix */
   uint64_t deep_lcp_direct;     /* irreducible deep LCPs computed by direct comparison */
   uint64_t deep_lcp_long;       /* ... that needed the block-wide comparison */
@@ -55,8 +55,9 @@ typedef struct caps_sa_gpu_stats {
   uint32_t key_bits;            /* leading bits of the packed prefix used as the sort key */
   uint32_t reserved;
   /* sharded construction only: */
-  float ms_partition;           /* pivots, pivot location, (key, suffix) all-to-all */
-  float ms_merge;               /* merge-path tree over the received runs */
+  float ms_partition;           /* pivots, partition pass and suffix all-to-all (merge mode: pivot location and
+                                   the (key, suffix) all-to-all) */
+  float ms_merge;               /* merge-path tree over the received runs (merge mode only) */
   uint64_t comm_bytes;          /* bytes this rank moved to other ranks */
   uint64_t shard_offset;        /* this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count) */
   uint64_t shard_count;
