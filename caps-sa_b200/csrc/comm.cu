@@ -110,6 +110,22 @@ void ThreadComm::all_gather_device(const void* send, void* recv, size_t bytes, c
 }
 
 // ---- SelfComm ---------------------------------------------------------------------------
+std::vector<void*> ThreadComm::open_peer_buffers(void* mine, cudaStream_t) {
+  // one process: the peers' addresses are usable as they are (peer access was enabled in the
+  // constructor where the ranks sit on different devices)
+  group_->slot(rank).ptr = mine;
+  group_->arrive_and_wait();
+  std::vector<void*> peers(static_cast<size_t>(world));
+  for (int p = 0; p < world; ++p) peers[static_cast<size_t>(p)] = const_cast<void*>(group_->slot(p).ptr);
+  group_->arrive_and_wait();  // everybody has read the slots before they are reused
+  return peers;
+}
+
+void ThreadComm::close_peer_buffers(const std::vector<void*>&, cudaStream_t st) {
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+  group_->arrive_and_wait();
+}
+
 void SelfComm::all_to_all_v(const void* send, const uint64_t* send_counts, void* recv, const uint64_t* recv_counts,
                             size_t elem_bytes, cudaStream_t st) {
   if (send_counts[0] != recv_counts[0]) fail("all_to_all_v: count mismatch");
@@ -117,6 +133,8 @@ void SelfComm::all_to_all_v(const void* send, const uint64_t* send_counts, void*
     CAPSB_CUDA(cudaMemcpyAsync(recv, send, send_counts[0] * elem_bytes, cudaMemcpyDeviceToDevice, st));
 }
 void SelfComm::all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t) { std::memcpy(out, in, bytes); }
+std::vector<void*> SelfComm::open_peer_buffers(void* mine, cudaStream_t) { return {mine}; }
+void SelfComm::close_peer_buffers(const std::vector<void*>&, cudaStream_t st) { CAPSB_CUDA(cudaStreamSynchronize(st)); }
 void SelfComm::all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) {
   if (bytes && send != recv) CAPSB_CUDA(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st));
 }
@@ -237,6 +255,38 @@ void NcclComm::all_gather_device(const void* send, void* recv, size_t bytes, cud
   if (!bytes) return;
   nccl_check(nccl().AllGather(send, recv, bytes, kNcclUint8, comm_, st), "ncclAllGather");
   bytes_sent += bytes * static_cast<size_t>(world - 1);
+}
+
+// One process per rank: the buffers cross the process boundary as CUDA IPC handles (all-gathered
+// as host bytes) and are mapped with peer access over NVLink.
+std::vector<void*> NcclComm::open_peer_buffers(void* mine, cudaStream_t st) {
+  cudaIpcMemHandle_t handle;
+  CAPSB_CUDA(cudaIpcGetMemHandle(&handle, mine));
+  std::vector<cudaIpcMemHandle_t> all(static_cast<size_t>(world));
+  all_gather_host(&handle, sizeof(handle), all.data(), st);
+  std::vector<void*> peers(static_cast<size_t>(world), nullptr);
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      peers[static_cast<size_t>(p)] = mine;
+      continue;
+    }
+    void* mapped = nullptr;
+    CAPSB_CUDA(cudaIpcOpenMemHandle(&mapped, all[static_cast<size_t>(p)], cudaIpcMemLazyEnablePeerAccess));
+    peers[static_cast<size_t>(p)] = mapped;
+  }
+  return peers;
+}
+
+void NcclComm::close_peer_buffers(const std::vector<void*>& peers, cudaStream_t st) {
+  CAPSB_CUDA(cudaStreamSynchronize(st));
+  // barrier: nobody unmaps (or reads its own buffer) before every rank's stores have completed
+  const uint32_t token = 1;
+  std::vector<uint32_t> tokens(static_cast<size_t>(world));
+  all_gather_host(&token, sizeof(token), tokens.data(), st);
+  for (int p = 0; p < world; ++p)
+    if (p != rank && peers[static_cast<size_t>(p)]) CAPSB_CUDA(cudaIpcCloseMemHandle(peers[static_cast<size_t>(p)]));
+  // second barrier: an owner may free its buffer only after every importer has unmapped it
+  all_gather_host(&token, sizeof(token), tokens.data(), st);
 }
 
 void NcclComm::all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t st) {

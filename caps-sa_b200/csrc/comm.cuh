@@ -43,6 +43,16 @@ struct Comm {
   // Every rank contributes `bytes` of device memory; `recv` (device) receives world * bytes.
   virtual void all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) = 0;
 
+  // Peer-visible buffers, for kernels that store straight into the other ranks' memory over
+  // NVLink (the fused partition pass, sharded_build.cu).  Collective: every rank passes a buffer
+  // it obtained from cudaMalloc itself (the base address of the allocation — what CUDA IPC can
+  // export) and gets, for every rank p, an address through which its kernels can write rank p's
+  // buffer (entry `rank` is `mine`).  close_peer_buffers is collective too: it synchronises `st`,
+  // waits until every rank has done so (all stores into every buffer have landed) and releases
+  // the mappings.
+  virtual std::vector<void*> open_peer_buffers(void* mine, cudaStream_t st) = 0;
+  virtual void close_peer_buffers(const std::vector<void*>& peers, cudaStream_t st) = 0;
+
   // bytes moved by this rank over the transport so far (for the NVLink roofline)
   uint64_t bytes_sent = 0;
 };
@@ -85,6 +95,8 @@ class ThreadComm : public Comm {
                     size_t elem_bytes, cudaStream_t st) override;
   void all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t st) override;
   void all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) override;
+  std::vector<void*> open_peer_buffers(void* mine, cudaStream_t st) override;
+  void close_peer_buffers(const std::vector<void*>& peers, cudaStream_t st) override;
 
  private:
   std::shared_ptr<ThreadGroup> group_;
@@ -106,6 +118,8 @@ class NcclComm : public Comm {
                     size_t elem_bytes, cudaStream_t st) override;
   void all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t st) override;
   void all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) override;
+  std::vector<void*> open_peer_buffers(void* mine, cudaStream_t st) override;
+  void close_peer_buffers(const std::vector<void*>& peers, cudaStream_t st) override;
 
  private:
   void* comm_ = nullptr;  // ncclComm_t
@@ -119,6 +133,8 @@ class SelfComm : public Comm {
                     size_t elem_bytes, cudaStream_t st) override;
   void all_gather_host(const void* in, size_t bytes, void* out, cudaStream_t st) override;
   void all_gather_device(const void* send, void* recv, size_t bytes, cudaStream_t st) override;
+  std::vector<void*> open_peer_buffers(void* mine, cudaStream_t st) override;
+  void close_peer_buffers(const std::vector<void*>& peers, cudaStream_t st) override;
 };
 
 }  // namespace capsb

@@ -21,6 +21,7 @@
 // ranks; rank r ends up owning the contiguous range [offset, offset + count) of SA and LCP.
 #include "comm.cuh"
 #include "merge_path.cuh"
+#include "partition.cuh"
 #include "pipeline.cuh"
 
 namespace capsb {
@@ -336,6 +337,33 @@ struct BucketSource {
   static constexpr uint64_t bytes_read_per_item() { return 1; }
 };
 
+// Keys of the suffixes of a text slice for the dedicated partition kernels (partition.cuh).
+struct SliceKeys {
+  PackedText pt;
+  uint64_t mask;
+  uint64_t base;
+  __device__ __forceinline__ uint64_t key(uint64_t i) const { return pt.window(base + i) & mask; }
+};
+
+// A device buffer straight from cudaMalloc (not from the arena): its address is the base of an
+// allocation, which is what CUDA IPC can export to the other ranks' processes.
+struct RawDeviceBuffer {
+  void* ptr = nullptr;
+  explicit RawDeviceBuffer(size_t bytes) {
+    const cudaError_t err = cudaMalloc(&ptr, bytes ? bytes : 256);
+    if (err != cudaSuccess) {
+      cudaGetLastError();
+      fail(std::string("out of device memory: cudaMalloc of the peer-visible bucket buffer failed: ") +
+           cudaGetErrorString(err));
+    }
+  }
+  ~RawDeviceBuffer() {
+    if (ptr) cudaFree(ptr);
+  }
+  RawDeviceBuffer(const RawDeviceBuffer&) = delete;
+  RawDeviceBuffer& operator=(const RawDeviceBuffer&) = delete;
+};
+
 }  // namespace
 
 template <class IdxT>
@@ -433,29 +461,81 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
       const uint64_t* ss = sorted_samples;
       launch_map(dev, st, world - 1, [=] __device__(uint64_t j) { pv[j] = ss[(j + 1) * kSamplesPerRank - 1]; });
     }
-    // ---- partition: the slice's suffixes grouped by bucket, in text order inside a bucket ----
-    DevBuf<IdxT> slice_idx(slice_count, st);
-    {
-      DevBuf<uint8_t> bucket_of(slice_count, st);
-      CAPSB_CUDA(cudaMemsetAsync(eng.radix.digit_total.get(), 0, kRadixSize * sizeof(uint64_t), st));
-      radix_pass<uint8_t, IdxT>(st, eng.radix, BucketSource<IdxT>{pt, key_mask, lo, pivots.get(), world - 1},
-                                slice_count, 0, bucket_of.get(), slice_idx.get());
-      CAPSB_CUDA(cudaMemcpyAsync(send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t),
-                                 cudaMemcpyDeviceToHost, st));
-      CAPSB_CUDA(cudaStreamSynchronize(st));
+    // CAPSB_SHARD_P2P=1 (experimental, off by default): the partition pass and the exchange as ONE
+    // kernel — the dedicated G-way partition (partition.cuh) stores every suffix index straight
+    // into its owner's bucket buffer over NVLink instead of grouping the slice locally and
+    // handing it to ncclSend/Recv.  Same bucket layout (runs by source rank, text order inside a
+    // run), so everything after it is unchanged.
+    const char* p2p_env = std::getenv("CAPSB_SHARD_P2P");
+    const bool p2p = p2p_env && p2p_env[0] == '1' && world <= static_cast<unsigned>(kPartMaxBuckets);
+    std::unique_ptr<RawDeviceBuffer> peer_bucket;  // the bucket's suffix indices in P2P mode
+    DevBuf<IdxT> bucket_idx;
+    const IdxT* bucket_suffixes = nullptr;
+    if (p2p) {
+      PartPivots piv{};
+      piv.count = world - 1;
+      if (world > 1) read_back(st, piv.p, pivots.get(), (world - 1) * sizeof(uint64_t));
+      const SliceKeys slice_keys{pt, key_mask, lo};
+      const Chunking ck = make_chunking(slice_count, kPartTile, static_cast<unsigned>(dev.sm_count) * 8);
+      DevBuf<uint64_t> hist(static_cast<uint64_t>(kPartMaxBuckets) * ck.blocks, st), totals(kPartMaxBuckets, st);
+      CAPSB_LAUNCH((partition_count_kernel<SliceKeys>), ck.blocks, kPartThreads, 0, st, slice_keys, slice_count, ck.chunk,
+                   piv, hist.get());
+      CAPSB_LAUNCH(partition_offsets_kernel, kPartMaxBuckets, 32, 0, st, hist.get(), ck.blocks, totals.get());
+      uint64_t h_totals[kPartMaxBuckets];
+      read_back(st, h_totals, totals.get(), sizeof(h_totals));
+      for (unsigned q = 0; q < world; ++q) send_counts[q] = h_totals[q];
+      exchange_counts();
+      clock.mark("partitioned");  // 2
+      peer_bucket = std::make_unique<RawDeviceBuffer>(bucket_count * sizeof(IdxT));
+      const std::vector<void*> peers = comm.open_peer_buffers(peer_bucket->ptr, st);
+      PartDestinations<IdxT> dst{};
+      for (unsigned q = 0; q < static_cast<unsigned>(kPartMaxBuckets); ++q) {
+        if (q >= world) {
+          dst.ptr[q] = static_cast<IdxT*>(peer_bucket->ptr);  // never written: no key maps to these buckets
+          continue;
+        }
+        uint64_t before = 0;  // what the ranks below this one send to rank q comes first in its bucket
+        for (unsigned s = 0; s < rank; ++s) before += matrix[static_cast<size_t>(s) * world + q];
+        dst.ptr[q] = static_cast<IdxT*>(peers[q]) + before;
+        if (q != rank) comm.bytes_sent += send_counts[q] * sizeof(IdxT);
+      }
+      if (slice_count)
+        CAPSB_LAUNCH((partition_scatter_kernel<IdxT, SliceKeys>), ck.blocks, kPartThreads, 0, st, slice_keys, slice_count,
+                     ck.chunk, lo, piv, hist.get(), dst);
+      comm.close_peer_buffers(peers, st);  // every rank's stores have landed in every bucket
+      bucket_suffixes = static_cast<const IdxT*>(peer_bucket->ptr);
+      clock.mark("exchanged");  // 3
+    } else {
+      // ---- partition: the slice's suffixes grouped by bucket, in text order inside a bucket ----
+      DevBuf<IdxT> slice_idx(slice_count, st);
+      {
+        DevBuf<uint8_t> bucket_of(slice_count, st);
+        CAPSB_CUDA(cudaMemsetAsync(eng.radix.digit_total.get(), 0, kRadixSize * sizeof(uint64_t), st));
+        radix_pass<uint8_t, IdxT>(st, eng.radix, BucketSource<IdxT>{pt, key_mask, lo, pivots.get(), world - 1},
+                                  slice_count, 0, bucket_of.get(), slice_idx.get());
+        CAPSB_CUDA(cudaMemcpyAsync(send_counts.data(), eng.radix.digit_total.get(), world * sizeof(uint64_t),
+                                   cudaMemcpyDeviceToHost, st));
+        CAPSB_CUDA(cudaStreamSynchronize(st));
+      }
+      exchange_counts();
+      clock.mark("partitioned");  // 2
+      // ---- collate: suffix indices move to the rank that owns their bucket ----------------------
+      bucket_idx.alloc(bucket_count, st);
+      comm.all_to_all_v(slice_idx.get(), send_counts.data(), bucket_idx.get(), recv_counts.data(), sizeof(IdxT), st);
+      slice_idx.release();
+      bucket_suffixes = bucket_idx.get();
+      clock.mark("exchanged");  // 3
     }
-    exchange_counts();
-    clock.mark("partitioned");  // 2
-    // ---- collate: suffix indices move to the rank that owns their bucket ----------------------
-    DevBuf<IdxT> bucket_idx(bucket_count, st);
-    comm.all_to_all_v(slice_idx.get(), send_counts.data(), bucket_idx.get(), recv_counts.data(), sizeof(IdxT), st);
-    slice_idx.release();
-    clock.mark("exchanged");  // 3
     // ---- bucket sort: keys come from the text again (each received run is in text order) ------
     bucket_keys.alloc(bucket_count, st);
     out.sa.alloc(bucket_count, st);
-    sort_suffixes_by_key<IdxT>(eng, SuffixListSource<IdxT>{pt, key_mask, bucket_idx.get()}, bucket_count, key_bits,
+    sort_suffixes_by_key<IdxT>(eng, SuffixListSource<IdxT>{pt, key_mask, bucket_suffixes}, bucket_count, key_bits,
                                bucket_keys.get(), out.sa.get());
+    bucket_idx.release();
+    if (peer_bucket) {  // cudaFree waits for the sort that read it
+      CAPSB_CUDA(cudaStreamSynchronize(st));
+      peer_bucket.reset();
+    }
     clock.mark("bucket sorted");  // 4
   } else {
     // ---- slice sort ------------------------------------------------------------------------

@@ -3,6 +3,8 @@ inside one process (caps_sa_gpu_construct_multi_*); listing device 0 several tim
 several ranks on one GPU, so the whole exchange logic — slice sort, pivots, all-to-all, bucket
 merge, rank exchange per refinement round, LCP round trip — is exercised on a one-GPU box.
 With more GPUs visible the same tests also spread the ranks over the devices."""
+import os
+
 import numpy as np
 import pytest
 
@@ -62,6 +64,25 @@ def test_sharded_matches_oracle(pkg, synth, case, ranks):
     check_shards(stats, len(text))
     assert np.array_equal(obj.SA(), want_sa), f"SA differs ({stats})"
     assert np.array_equal(obj.LCP(), want_lcp), f"LCP differs ({stats})"
+
+
+# The fused partition pass (CAPSB_SHARD_P2P=1: suffix indices stored straight into the owners'
+# buckets, csrc/partition.cuh) is experimental and has not run on a GPU yet; its tests are opt-in
+# (CAPSB_TEST_P2P=1) until it has.
+p2p_opt_in = pytest.mark.skipif(os.environ.get("CAPSB_TEST_P2P") != "1", reason="experimental path: set CAPSB_TEST_P2P=1")
+
+
+@p2p_opt_in
+@pytest.mark.parametrize("ranks", [1, 2, 3, 8])
+@pytest.mark.parametrize("case", ["acgt_1M", "genome_like_2M", "bytes256_300k", "fibonacci_200k", "allA_50k"])
+def test_sharded_p2p_partition_matches_oracle(pkg, synth, case, ranks, monkeypatch):
+    monkeypatch.setenv("CAPSB_SHARD_P2P", "1")
+    text, want_sa, want_lcp = oracle(case, synth)
+    obj = pkg.SuffixArray(text, devices=device_list(pkg, ranks))
+    obj.construct()
+    check_shards(obj._rank_stats, len(text))
+    assert np.array_equal(obj.SA(), want_sa)
+    assert np.array_equal(obj.LCP(), want_lcp)
 
 
 @pytest.mark.parametrize("ranks", [2, 3])
