@@ -165,3 +165,22 @@ def test_one_process_per_gpu_nccl(pkg):
          "--master-addr", "127.0.0.1", "--master-port", "29731", os.path.join(root, "tools", "sharded_check.py")],
         capture_output=True, text=True, timeout=900)
     assert proc.returncode == 0 and "SHARDED_CHECK PASSED" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
+
+
+@p2p_opt_in
+def test_one_process_per_gpu_nccl_p2p_partition(pkg):
+    """The fused partition pass under torchrun: the bucket buffers cross the process boundary as
+    CUDA IPC handles (needs at least two GPUs)."""
+    import subprocess
+    import sys
+
+    visible = pkg.lib().caps_sa_gpu_device_count()
+    if visible < 2:
+        pytest.skip("needs >= 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    world = min(visible, 4)
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29733", os.path.join(root, "tools", "sharded_check.py")],
+        capture_output=True, text=True, timeout=900, env=dict(os.environ, CAPSB_SHARD_P2P="1"))
+    assert proc.returncode == 0 and "SHARDED_CHECK PASSED" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
