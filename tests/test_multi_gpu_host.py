@@ -88,3 +88,35 @@ def test_host_side_world2_gloo(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_bind_to_gpu_cpus_is_a_noop_without_nvml():
+    """bench.py's NUMA binding is strictly an optimisation: without a GPU / NVML it reports None and
+    leaves the process affinity alone."""
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+
+    graft.load_package()
+    from caps_sa_b200 import multi_gpu
+
+    before = os.sched_getaffinity(0)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the binding may legitimately change the affinity")
+    assert multi_gpu.bind_to_gpu_cpus(0) is None
+    assert os.sched_getaffinity(0) == before
+
+
+def test_slice_bounds_cover_the_text():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as graft
+
+    graft.load_package()
+    from caps_sa_b200 import multi_gpu
+
+    for n, world in [(0, 3), (7, 8), (100, 1), (3_100_000_000, 8), (12_000_000_001, 7)]:
+        at = 0
+        for r in range(world):
+            lo, hi = multi_gpu.slice_bounds(n, world, r)
+            assert lo == at and hi >= lo
+            at = hi
+        assert at == n
