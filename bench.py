@@ -47,8 +47,12 @@ WORKLOADS = {
 # `ncu --set full` capture (profiles/r01/scatter_ncu_full_v4.csv: dram__bytes_read.sum 1.310726 GB +
 # dram__bytes_write.sum 1.234758 GB per launch over 100 000 001 (u64, u32) pairs = 24 B each)
 NCU_TRAFFIC_RATIO = (1.310726e9 + 1.234758e9) / (24.0 * 100_000_001)
-CPU_SAMPLE = 32_000_000   # prefix of the workload the CPU reference is timed on
+CPU_SAMPLE = 310_000_000  # symbols the CPU reference is timed on: 1/10 of the 3.1 Gbp workload (10-15 s per construct())
 CPU_SUBPROBLEMS = 256      # the reference's best case in SURVEY.md §6 (default 8192 is ~2x slower)
+REF_BUILD = ("oracle/_ref built by oracle/Makefile: g++ -std=c++17 -Ofast -funroll-loops -march=x86-64-v3 -fopenmp -DNDEBUG "
+             "(the reference's CMakeLists.txt:49 has -Ofast -mavx2 -funroll-loops -march=native; native is replaced by "
+             "x86-64-v3 = AVX2/BMI2 so the binary built in the build container runs on the GPU box's host); "
+             "OpenMP stand-in for ParlayLib's three scheduling calls")
 
 
 def make_text(pkg, spec, n):
@@ -130,13 +134,38 @@ def cpu_reference_run(text, subproblems, threads):
     return time.time() - t0, "port"
 
 
+def verify_result(text, sa, lcp):
+    """Independent check of a finished (SA, LCP) against the text: oracle/sa_check.c
+    caps_check_sa_lcp_mt — permutation, suffix order through the inverse permutation, LCP by
+    Kasai's walk (the predicate of the reference's is_sorted, src/Suffix_Array.cpp:512-536).
+    Runs after the timed regions; a non-zero code fails the run."""
+    import oracle_lib
+
+    t0 = time.time()
+    code, bad = oracle_lib.check_sa_lcp_mt(text, sa, lcp)
+    return {"checker": "oracle/sa_check.c caps_check_sa_lcp_mt (permutation + suffix order via ISA + Kasai LCP, OpenMP)",
+            "what": "the SA and LCP arrays the last end-to-end step left in the host buffers, all n entries",
+            "code": int(code), "first_bad_position": int(bad) if code else None, "n": int(len(text)),
+            "seconds": round(time.time() - t0, 1)}
+
+
+def sample_text(pkg, spec, n, sample_n):
+    """The CPU arm's input: the workload recipe at sample size (same repeat structure, scaled), not a
+    prefix of the full text — so `--impl reference` need not generate all n symbols."""
+    if sample_n >= n:
+        return make_text(pkg, spec, n)
+    if spec["kind"] == "genome_like":
+        return pkg.synth.genome_like(sample_n, seed=spec["seed"], scale=sample_n / 3.1e9)
+    return make_text(pkg, spec, sample_n)
+
+
 def run_reference_arm(args, spec, n):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pkg = graft.load_package()
     sample_n = min(n, args.cpu_sample)
-    text = make_text(pkg, spec, sample_n)  # same recipe, sample-sized
+    text = sample_text(pkg, spec, n, sample_n)
     threads = os.cpu_count() or 1
     times = []
     kind = "reference"
@@ -151,10 +180,13 @@ def run_reference_arm(args, spec, n):
         "impl": "reference", "metric": "sa_lcp_suffixes_per_sec", "value": value, "unit": "suffixes/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec['desc']}", "n": n, "idx_bytes": 4},
+        "config": {"workload": f"{args.workload}: {spec['desc']}", "n": sample_n, "sample_of": n, "idx_bytes": 4,
+                   "note": "n is what this arm constructs per step: the workload recipe at sample size "
+                           "(the CPU reference needs minutes per construct() at the full n)"},
         "cpu_baseline": {"value": value, "unit": "suffixes/s", "cores": threads, "kind": kind,
-                         "sample": f"first {sample_n} symbols of the workload recipe, subproblem_count={args.cpu_subproblems}, "
-                                   f"PARLAY_NUM_THREADS={threads} (OpenMP stand-in for ParlayLib), construct() only"},
+                         "seconds_per_step": per_step, "build": REF_BUILD,
+                         "sample": f"the workload recipe at {sample_n} symbols (1/{max(1, round(n / sample_n))} of n={n}), "
+                                   f"subproblem_count={args.cpu_subproblems}, PARLAY_NUM_THREADS={threads}, construct() only"},
         "e2e": {"value": value, "unit": "suffixes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -172,6 +204,7 @@ def main():
     ap.add_argument("--cpu-subproblems", type=int, default=CPU_SUBPROBLEMS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
+    ap.add_argument("--no-verify", action="store_true", help="profiling runs only: skip the post-run check of SA/LCP")
     args = ap.parse_args()
     spec = WORKLOADS[args.workload]
     n = int(args.n) if args.n else spec["n"]
@@ -198,9 +231,15 @@ def main():
     pkg = graft.load_package()
     if world > 1:
         from caps_sa_b200 import multi_gpu  # sharded path (torch.distributed plumbing + our kernels)
-        multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks, NCU_TRAFFIC_RATIO)
+        out = multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks, NCU_TRAFFIC_RATIO)
         dist.barrier()
         dist.destroy_process_group()
+        if out is not None:  # rank 0: check the assembled result of the last end-to-end step, then report
+            line, (text_host, sa_host, lcp_host) = out
+            line["verified"] = None if args.no_verify else verify_result(text_host, sa_host, lcp_host)
+            print(json.dumps(line), flush=True)
+            if line["verified"] and line["verified"]["code"] != 0:
+                raise SystemExit("bench.py: the benchmarked SA/LCP failed verification (see \"verified\")")
         return
 
     t_gen = time.time()
@@ -274,8 +313,20 @@ def main():
     e2e_ms = max(ev2.elapsed_time(ev3) / args.steps, e2e_wall_ms)
     clocks = sampler.stop()
 
-    # sanity: the e2e result equals the device-resident result (same kernels)
-    same = None if args.no_e2e else bool(torch.equal(d_sa.cpu()[:1_000_000], sa_pin[:1_000_000]))
+    # the device-resident leg left the same arrays in HBM as the end-to-end leg left in the host buffers
+    # (all n entries of SA and LCP, compared on the device piece by piece)
+    same = None
+    if not args.no_e2e:
+        same = True
+        piece = 1 << 28
+        for lo in range(0, n, piece):
+            hi = min(n, lo + piece)
+            same = same and bool(torch.equal(d_sa[lo:hi], sa_pin[lo:hi].cuda(non_blocking=True)))
+            same = same and bool(torch.equal(d_lcp[lo:hi], lcp_pin[lo:hi].cuda(non_blocking=True)))
+    # independent check of what was benchmarked (outside the timed regions)
+    verified = None
+    if not (args.no_e2e or args.no_verify):
+        verified = verify_result(text_np, sa_host, lcp_host)
 
     peak, peak_kind = load_peaks()
     achieved = (scatter_bytes / 1e9) / (scatter_ms / 1e3) if scatter_ms > 0 else None
@@ -296,11 +347,11 @@ def main():
     if not args.no_cpu_baseline:
         sample_n = min(n, args.cpu_sample)
         threads = os.cpu_count() or 1
-        secs, kind = cpu_reference_run(text_np[:sample_n].copy(), args.cpu_subproblems, threads)
+        secs, kind = cpu_reference_run(sample_text(pkg, spec, n, sample_n), args.cpu_subproblems, threads)
         cpu_baseline = {"value": sample_n / secs, "unit": "suffixes/s", "cores": threads, "kind": kind,
-                        "seconds": secs,
-                        "sample": f"first {sample_n} symbols of the workload text, subproblem_count={args.cpu_subproblems}, "
-                                  f"PARLAY_NUM_THREADS={threads} (OpenMP stand-in for ParlayLib), construct() only"}
+                        "seconds": secs, "build": REF_BUILD,
+                        "sample": f"the workload recipe at {sample_n} symbols (1/{max(1, round(n / sample_n))} of n={n}), "
+                                  f"subproblem_count={args.cpu_subproblems}, PARLAY_NUM_THREADS={threads}, construct() only, one run"}
 
     line = {
         "metric": "sa_lcp_suffixes_per_sec", "value": n / (dev_ms / 1e3), "unit": "suffixes/s",
@@ -312,11 +363,14 @@ def main():
                    "refine_rounds": last_stats["refine_rounds"]},
         "e2e": {"value": n / (e2e_ms / 1e3), "unit": "suffixes/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": n, "d2h_bytes_per_step": 2 * 4 * n, "matches_device_result": same},
+        "verified": verified,
         "gpu_launches": int(launches),
         "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+    if (verified and verified["code"] != 0) or same is False:
+        raise SystemExit("bench.py: the benchmarked SA/LCP failed verification (see \"verified\" / \"matches_device_result\")")
 
 
 if __name__ == "__main__":

@@ -112,28 +112,26 @@ def _check(rc: int) -> None:
 
 
 class PinnedArray:
-    """numpy view over pinned host memory from caps_sa_gpu_host_alloc."""
+    """numpy array over pinned host memory from caps_sa_gpu_host_alloc.
 
-    def __init__(self, count: int, dtype):
+    The memory belongs to the buffer object the array is built on, not to this wrapper: it is
+    returned to the driver when the last array (or view) that refers to it has gone, so
+    ``arr = SuffixArray(t).SA()`` stays valid after the SuffixArray is collected."""
+
+    def __init__(self, count: int, dtype, _alloc=None, _free=None):
+        import weakref
+
         self.dtype = np.dtype(dtype)
         self.nbytes = max(1, count * self.dtype.itemsize)
-        self.ptr = lib().caps_sa_gpu_host_alloc(self.nbytes)
+        alloc = _alloc or lib().caps_sa_gpu_host_alloc
+        free = _free or lib().caps_sa_gpu_host_free
+        self.ptr = alloc(self.nbytes)
         if not self.ptr:
             raise CapsSaError("pinned host allocation failed: " + lib().caps_sa_gpu_last_error().decode())
         buf = (C.c_char * self.nbytes).from_address(self.ptr)
+        # numpy keeps `buf` alive through .base for as long as any view of the array exists
+        self._finalizer = weakref.finalize(buf, free, self.ptr)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=count)
-
-    def free(self) -> None:
-        if self.ptr:
-            self.array = None
-            lib().caps_sa_gpu_host_free(self.ptr)
-            self.ptr = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
 
 
 class Engine:

@@ -152,7 +152,8 @@ def bind_to_gpu_cpus(device_index: int):
 # ---- bench.py, N > 1 -----------------------------------------------------------------------
 def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, traffic_ratio=None):
     """bench.py's multi-rank arm: same JSON contract, time = max over ranks, value = n / time.
-    The text is fixed (strong scaling): every rank generates the same synthetic text."""
+    The text is fixed (strong scaling): every rank generates the same synthetic text.
+    Returns (json line, (text, SA, LCP) host arrays) on rank 0, None on the other ranks."""
     rank = dist.get_rank()
     world = dist.get_world_size()
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -268,7 +269,7 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, tra
     total_comm = sum_over_ranks(comm_bytes)
     largest = max(c for _, c in layout)
     if rank != 0:
-        return
+        return None
     peak, peak_kind = load_peaks()
     achieved = (scatter_bytes / 1e9) / (scatter_ms / 1e3) if scatter_ms > 0 else None
     line = {
@@ -296,4 +297,6 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, tra
                      "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches)},
         "cpu_baseline": None, "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    # rank 0 verifies the arrays all ranks wrote into the shared host buffers and prints the line
+    # once the process group is gone (bench.py), so no rank waits in a collective meanwhile
+    return line, (text_host, sa_host, lcp_host)

@@ -42,6 +42,12 @@ void caps_port_map_acgt(char* text, uint64_t n);
 int caps_check_sa_lcp(const char* text, uint64_t n, const void* sa, const void* lcp,
                       int idx_bytes, uint64_t* bad_pos);
 
+/* caps_check_sa_lcp with OpenMP loops (Kasai's walk restarted per range of text positions) and
+ * an inverse permutation at the input's index width: the form bench.py applies to the 3.1 G
+ * suffix results.  Same codes. */
+int caps_check_sa_lcp_mt(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
+                         uint64_t* bad_pos);
+
 /* The same validation for a text that is its first `period` (<= 4096) bytes repeated, with OpenMP
  * loops and the LCP from the closed form for periodic texts (sa_check.c) — for the 1 Gbp
  * periodic text of BASELINE config 4, where the sequential walk above takes minutes.

@@ -148,6 +148,102 @@ done:
   return rc;
 }
 
+/* Multi-threaded form of caps_check_sa_lcp for the sizes bench.py builds (3.1 G suffixes): the
+ * same three predicates — permutation, suffix order through the inverse permutation, LCP by
+ * Kasai's walk — as OpenMP loops.  Kasai's walk is sequential in the text position (h drops by
+ * at most one per step); here the text is cut into `pieces` ranges of positions and every range
+ * starts its own walk at h = 0, which costs one from-scratch comparison per range and changes
+ * nothing else.  The inverse permutation is stored at the index width of the input (4 bytes for
+ * a 32-bit suffix array), so 3.1 G suffixes need 12.4 GB on top of the arrays being checked.
+ * Same return codes; bad_pos = the smallest offending SA position of the failing predicate. */
+int caps_check_sa_lcp_mt(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
+                         uint64_t* bad_pos) {
+  if ((idx_bytes != 4 && idx_bytes != 8) || !text || !sa || !lcp) return 4;
+  if (n == 0) return 0;
+  const signed char* t = (const signed char*)text;
+  const int w = idx_bytes;
+  void* rank = malloc(n * (size_t)w); /* rank[s] = SA position of suffix s */
+  unsigned char* seen = calloc((n + 7) / 8, 1);
+  if (!rank || !seen) {
+    free(rank), free(seen);
+    return 4;
+  }
+  int rc = 0;
+  uint64_t bad = UINT64_MAX;
+#define CAPS_FAIL(code, where)                       \
+  do {                                               \
+    _Pragma("omp critical(caps_check_mt_fail)") {    \
+      if ((where) < bad) rc = (code), bad = (where); \
+    }                                                \
+  } while (0)
+#define RANK_OF(s) (w == 4 ? (uint64_t)((const uint32_t*)rank)[s] : ((const uint64_t*)rank)[s])
+
+#pragma omp parallel for schedule(static)
+  for (uint64_t k = 0; k < n; ++k) { /* permutation of [0, n) */
+    const uint64_t s = get_idx(sa, w, k);
+    if (s >= n) {
+      CAPS_FAIL(1, k);
+      continue;
+    }
+    const unsigned char bit = (unsigned char)(1u << (s & 7u));
+    if (__atomic_fetch_or(&seen[s >> 3], bit, __ATOMIC_RELAXED) & bit) {
+      CAPS_FAIL(1, k);
+      continue;
+    }
+    if (w == 4)
+      ((uint32_t*)rank)[s] = (uint32_t)k;
+    else
+      ((uint64_t*)rank)[s] = k;
+  }
+  if (rc) goto done;
+
+#pragma omp parallel for schedule(static)
+  for (uint64_t k = 1; k < n; ++k) { /* suffix a must precede suffix b; the empty suffix precedes everything */
+    const uint64_t a = get_idx(sa, w, k - 1), b = get_idx(sa, w, k);
+    int ok;
+    if (t[a] != t[b]) {
+      ok = t[a] < t[b];
+    } else if (a + 1 == n) {
+      ok = 1;
+    } else if (b + 1 == n) {
+      ok = 0;
+    } else {
+      ok = RANK_OF(a + 1) < RANK_OF(b + 1);
+    }
+    if (!ok) CAPS_FAIL(2, k);
+  }
+  if (rc) goto done;
+
+  if (get_idx(lcp, w, 0) != 0) CAPS_FAIL(3, 0);
+  {
+    uint64_t pieces = n / 65536 + 1;
+    if (pieces > 4096) pieces = 4096;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (uint64_t p = 0; p < pieces; ++p) {
+      const uint64_t lo = n / pieces * p, hi = p + 1 == pieces ? n : n / pieces * (p + 1);
+      uint64_t h = 0;
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint64_t k = RANK_OF(i);
+        if (k == 0) {
+          h = 0;
+          continue;
+        }
+        const uint64_t j = get_idx(sa, w, k - 1);
+        while (i + h < n && j + h < n && t[i + h] == t[j + h]) ++h;
+        if (get_idx(lcp, w, k) != h) CAPS_FAIL(3, k);
+        if (h) --h;
+      }
+    }
+  }
+
+done:
+#undef CAPS_FAIL
+#undef RANK_OF
+  if (rc && bad_pos) *bad_pos = bad;
+  free(rank), free(seen);
+  return rc;
+}
+
 typedef struct {
   const signed char* t;
   uint64_t n;

@@ -91,14 +91,10 @@ Suffix_Array<T_idx_>::Suffix_Array(const char* const T, const idx_t n, const idx
     max_context_(max_context),
     constructed_(false)
 {
-    // The reference rejects p > n (src/Suffix_Array.cpp:33-37); its p is clamped to n / 16
-    // first (:24), so the check can only trigger through that clamp being bypassed.  Kept for
-    // interface parity on the raw argument.
-    if(subproblem_count > n && n >= 16)
-    {
-        std::cerr << "Incompatible subproblem-count. Aborting.\n";
-        std::exit(EXIT_FAILURE);
-    }
+    // The reference derives p = min(subproblem_count ? subproblem_count : 8192, n / 16) (src/Suffix_Array.cpp:24)
+    // before it tests p > n (:33-37), so that test never fires for any argument (and n < 16 dies
+    // earlier, by a division by zero, :27): every subproblem count is accepted.  Here the count is a
+    // hint the construction ignores — the output does not depend on it.
 }
 
 

@@ -48,6 +48,8 @@ def port():
         lib.caps_port_map_acgt.restype = None
         lib.caps_check_sa_lcp.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp.restype = C.c_int
+        lib.caps_check_sa_lcp_mt.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
+        lib.caps_check_sa_lcp_mt.restype = C.c_int
         lib.caps_check_sa_lcp_periodic.argtypes = [p, u64, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp_periodic.restype = C.c_int
         lib.caps_naive_sa_lcp.argtypes = [p, u64, p, p]
@@ -124,6 +126,18 @@ def check_sa_lcp(text, sa: np.ndarray, lcp: np.ndarray):
     bad = C.c_uint64(0)
     rc = port().caps_check_sa_lcp(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
                                   sa.dtype.itemsize, C.byref(bad))
+    return rc, bad.value
+
+
+def check_sa_lcp_mt(text, sa: np.ndarray, lcp: np.ndarray):
+    """check_sa_lcp with OpenMP loops (oracle/sa_check.c: caps_check_sa_lcp_mt): what bench.py applies
+    to its full-size results.  No copies are made: pass contiguous arrays."""
+    t = _as_text(text)
+    assert sa.flags.c_contiguous and lcp.flags.c_contiguous
+    assert sa.dtype == lcp.dtype and sa.dtype in (np.uint32, np.uint64)
+    bad = C.c_uint64(0)
+    rc = port().caps_check_sa_lcp_mt(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
+                                     sa.dtype.itemsize, C.byref(bad))
     return rc, bad.value
 
 

@@ -74,3 +74,31 @@ def test_class_header_keeps_reference_surface():
     impl = open(os.path.join(ROOT, "src", "Suffix_Array.cpp")).read()
     assert "template class CaPS_SA::Suffix_Array<uint32_t>;" in impl
     assert "template class CaPS_SA::Suffix_Array<uint64_t>;" in impl
+
+
+def test_pinned_array_memory_outlives_its_wrapper(pkg):
+    """The numpy array handed out by SuffixArray.SA()/LCP() owns the pinned block through its
+    buffer: the block is freed when the last view goes, not when the wrapper does."""
+    import ctypes as C
+    import gc
+
+    import numpy as np
+
+    freed, keep = [], []
+
+    def alloc(nbytes):
+        keep.append(C.create_string_buffer(nbytes))
+        return C.addressof(keep[-1])
+
+    pa = pkg.PinnedArray(10, np.uint32, _alloc=alloc, _free=freed.append)
+    arr = pa.array
+    view = arr[2:5]
+    del pa
+    gc.collect()
+    assert freed == []
+    del arr
+    gc.collect()
+    assert freed == []
+    del view
+    gc.collect()
+    assert freed == [C.addressof(keep[0])]

@@ -232,6 +232,135 @@ def test_bounded_context(pkg, engine, synth, case, ctx):
         assert np.array_equal(pad[ref_sa.astype(np.int64) + j], pad[sa.astype(np.int64) + j])
 
 
+# ---- device-resident entry points (what bench.py's `value` times) ---------------------------------
+def _device_construct(pkg, engine, text, idx_bytes, sharded=False):
+    import torch
+
+    n = len(text)
+    dt = torch.int32 if idx_bytes == 4 else torch.int64
+    d_text = torch.from_numpy(text.copy()).cuda()
+    stream = torch.cuda.current_stream()
+    if sharded:  # the sharded device entry point with a one-rank communicator; shard = everything
+        engine.comm_init(bytes(128), 0, 1)
+        engine.construct_sharded_device(d_text.data_ptr(), n, idx_bytes, stream.cuda_stream)
+        st = engine.stats()
+        assert (st["shard_offset"], st["shard_count"]) == (0, n)
+        d_sa = torch.empty(n, dtype=dt, device="cuda")
+        d_lcp = torch.empty(n, dtype=dt, device="cuda")
+        engine.shard_copy(d_sa.data_ptr(), d_lcp.data_ptr(), to_host=False)
+    else:
+        d_sa = torch.empty(n, dtype=dt, device="cuda")
+        d_lcp = torch.empty(n, dtype=dt, device="cuda")
+        engine.construct_device(d_text.data_ptr(), n, d_sa.data_ptr(), d_lcp.data_ptr(), idx_bytes, stream.cuda_stream)
+    torch.cuda.synchronize()
+    ndt = np.uint32 if idx_bytes == 4 else np.uint64
+    return d_sa.cpu().numpy().view(ndt), d_lcp.cpu().numpy().view(ndt)
+
+
+@pytest.mark.parametrize("sharded", [False, True])
+@pytest.mark.parametrize("idx_bytes", [4, 8])
+@pytest.mark.parametrize("case", ["genome_like_2M", "fibonacci_400k", "bytes256_500k", "allA_100k"])
+def test_device_resident_entry_points_match_oracle(pkg, synth, case, idx_bytes, sharded):
+    """caps_sa_gpu_construct_device_u32/u64 and caps_sa_gpu_construct_sharded_device_u32/u64: text,
+    SA and LCP stay in HBM; compared with the oracle like the host-buffer calls."""
+    text, p = CASES[case](synth)
+    text = text[:600_000] if idx_bytes == 8 else text
+    want_sa, want_lcp = oracle_sa_lcp(text, p, idx_bytes=idx_bytes)
+    eng = pkg.Engine(0)
+    try:
+        sa, lcp = _device_construct(pkg, eng, text, idx_bytes, sharded)
+    finally:
+        eng.close()
+    assert np.array_equal(sa, want_sa), "SA differs"
+    assert np.array_equal(lcp, want_lcp), "LCP differs"
+
+
+def test_golden_digest_100M_random(pkg, engine, synth):
+    """sha256 of the reference's dump for 100 Mbp random ACGT (numpy seed 3)."""
+    with open(os.path.join(GOLDEN_DIR, "golden_hashes.json")) as f:
+        gold = json.load(f)
+    want = gold["survey_appendix_A"]["acgt_seed3_100M_dump_sha256"]
+    assert want == "4878e2221dadb4144eeb4984bfe3f3602f64cd60883e73c8147c17bb22af6c1a"
+    text = synth.random_acgt(100_000_000, 3)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    h = hashlib.sha256()
+    h.update(np.uint64(len(text)).tobytes())
+    h.update(sa.data)
+    h.update(lcp.data)
+    assert h.hexdigest() == want, stats
+
+
+def test_config1_ecoli_sized_through_cli(pkg, synth, tmp_path):
+    """BASELINE config 1 at its own size (4.64 Mbp FASTA through the CLI with a small subproblem
+    count) against the reference CLI on the same file."""
+    raw = synth.ecoli_like_fasta(seed=1)
+    src = tmp_path / "ecoli_like.fa"
+    raw.tofile(src)
+    out_gpu = tmp_path / "gpu.bin"
+    proc = subprocess.run([os.path.join(ROOT, "bin", "caps_sa"), str(src), str(out_gpu), "64"],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "caps_sa_ref")
+    if os.path.exists(ref_cli):
+        out_cpu = tmp_path / "cpu.bin"
+        subprocess.run([ref_cli, str(src), str(out_cpu), "64"], check=True, capture_output=True)
+        assert out_gpu.read_bytes() == out_cpu.read_bytes()
+    else:
+        mapped = synth.map_acgt(raw)
+        sa = np.fromfile(out_gpu, dtype=np.uint32, offset=8, count=len(mapped))
+        lcp = np.fromfile(out_gpu, dtype=np.uint32, offset=8 + 4 * len(mapped), count=len(mapped))
+        assert oracle_lib.check_sa_lcp_mt(mapped, sa, lcp) == (0, 0)
+
+
+@pytest.mark.timeout(900)
+def test_u32_indices_above_2_to_31(pkg, synth):
+    """32-bit indices are used up to n = 2^32 - 1 (reference src/main.cpp:76): a text with more than
+    2^31 suffixes exercises every index beyond the sign bit.  Checked by the independent validator."""
+    n = (1 << 31) + 100_000_123
+    text = synth.genome_like(n, seed=9, scale=n / 3.1e9)
+    obj = pkg.SuffixArray(text)
+    obj.construct()
+    sa, lcp = obj.SA(), obj.LCP()
+    assert sa.dtype == np.uint32 and int(sa.max()) == n - 1
+    assert oracle_lib.check_sa_lcp_mt(text, sa, lcp) == (0, 0), obj.stats()
+
+
+def test_cli_accepts_subproblem_count_above_n(pkg, synth, tmp_path):
+    """The reference clamps its subproblem count to n / 16 before it is ever compared with n
+    (src/Suffix_Array.cpp:24,33-37), so `caps_sa small.fa out 8192` on a 1000-byte file succeeds."""
+    raw = synth.random_acgt(1000, 77)
+    src = tmp_path / "small.txt"
+    raw.tofile(src)
+    out_gpu = tmp_path / "gpu.bin"
+    proc = subprocess.run([os.path.join(ROOT, "bin", "caps_sa"), str(src), str(out_gpu), "8192"],
+                          capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr
+    ref_cli = os.path.join(ROOT, "oracle", "_ref", "caps_sa_ref")
+    if os.path.exists(ref_cli):
+        out_cpu = tmp_path / "cpu.bin"
+        subprocess.run([ref_cli, str(src), str(out_cpu), "8192"], check=True, capture_output=True)
+        assert out_gpu.read_bytes() == out_cpu.read_bytes()
+    sa, lcp = oracle_lib.port_sa_lcp(synth.map_acgt(raw), subproblems=8192)
+    assert out_gpu.read_bytes() == oracle_lib.dump_bytes(len(raw), sa, lcp)
+
+
+def test_result_arrays_outlive_the_object(pkg, engine, synth):
+    """SA()/LCP() are views of pinned memory; they must stay valid after the SuffixArray is gone."""
+    import gc
+
+    text = synth.random_acgt(200_000, 5)
+    obj = pkg.SuffixArray(text, engine=engine)
+    obj.construct()
+    sa, lcp = obj.SA(), obj.LCP()
+    want_sa, want_lcp = sa.copy(), lcp.copy()
+    del obj
+    gc.collect()
+    junk = [pkg.PinnedArray(200_000, np.uint32) for _ in range(4)]  # would reuse freed pinned blocks
+    for j in junk:
+        j.array[:] = 0xFFFFFFFF
+    assert np.array_equal(sa, want_sa) and np.array_equal(lcp, want_lcp)
+
+
 # ---- CLI: same file in, same file out ----------------------------------------------------------------
 def test_cli_dump_matches_reference_cli(pkg, synth, tmp_path):
     raw = synth.ecoli_like_fasta(seed=1, bases=400_000)
