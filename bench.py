@@ -66,6 +66,65 @@ def make_text(pkg, spec, n):
     raise ValueError(kind)
 
 
+# Kernel classes timed inside the library (CUDA events around every launch, on the launching stream):
+# stats prefix -> (name, what one launch's algorithmic bytes are)
+KERNEL_CLASSES = {
+    "scatter": ("radix_scatter_kernel", "(u64 key, u32 suffix) pairs read once and written once: 24 B per pair"),
+    "msd_scatter_a": ("msd_scatter_kernel, level A", "text window read (~1 B) + one 8-byte record written per suffix"),
+    "msd_scatter_b": ("msd_scatter_kernel, level B", "one 8-byte record read and written per suffix: 16 B"),
+    "msd_local": ("msd_local_kernel", "8-byte record read, 8-byte key + 4-byte suffix written: 20 B per suffix"),
+    "msd_hist": ("msd_hist_kernel", "text window (level A) or one 8-byte record (level B) read per suffix"),
+}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch over the algorithmic bytes of the launch, from the
+# committed `ncu --set full` captures (profiles/): filled in per kernel class as they are captured
+NCU_TRAFFIC = {
+    "scatter": (NCU_TRAFFIC_RATIO, "profiles/r01/scatter_ncu_full_v4.csv"),
+}
+
+
+class KernelClassTimes:
+    """Accumulates the per-kernel-class launch times / bytes / launch counts of engine.stats()."""
+
+    def __init__(self):
+        self.ms = {k: 0.0 for k in KERNEL_CLASSES}
+        self.bytes = {k: 0 for k in KERNEL_CLASSES}
+        self.launches = {k: 0 for k in KERNEL_CLASSES}
+
+    def add(self, st):
+        for k in KERNEL_CLASSES:
+            ms_key, b_key, l_key = (("ms_scatter", "scatter_bytes", "scatter_launches") if k == "scatter"
+                                    else (f"ms_{k}", f"{k}_bytes", f"{k}_launches"))
+            self.ms[k] += st.get(ms_key, 0.0)
+            self.bytes[k] += st.get(b_key, 0)
+            self.launches[k] += st.get(l_key, 0)
+
+    def report(self, peak, peak_kind, steps, step_ms):
+        table = {}
+        for k, (name, what) in KERNEL_CLASSES.items():
+            if self.launches[k] == 0 or self.ms[k] <= 0:
+                continue
+            gbs = self.bytes[k] / 1e9 / (self.ms[k] / 1e3)
+            table[k] = {"kernel": name, "launches": self.launches[k], "ms_per_step": self.ms[k] / steps,
+                        "achieved_GBps": gbs, "frac": gbs / peak, "share_of_step": self.ms[k] / steps / step_ms,
+                        "algorithmic_bytes": what}
+        if not table:
+            return None, table
+        top = max(table, key=lambda k: table[k]["ms_per_step"])
+        t = table[top]
+        ratio, source = NCU_TRAFFIC.get(top, (None, None))
+        per_launch = self.bytes[top] / self.launches[top]
+        roofline = {"kernel": t["kernel"], "bound": "hbm", "achieved": t["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                    "frac": t["frac"], "peak_source": peak_kind,
+                    "traffic": ratio * per_launch if ratio else None,
+                    "traffic_source": (f"ncu --set full capture of this kernel ({source}): dram read + write = {ratio:.3f} x "
+                                       "algorithmic bytes, scaled to this run's mean launch") if ratio else
+                                      "no ncu --set full capture of this kernel committed yet",
+                    "launches_timed": self.launches[top], "avg_launch_ms": self.ms[top] / self.launches[top],
+                    "share_of_step": t["share_of_step"], "algorithmic_bytes_per_launch": per_launch,
+                    "algorithmic_bytes": t["algorithmic_bytes"]}
+        return roofline, table
+
+
 class ClockSampler:
     """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
 
@@ -231,7 +290,7 @@ def main():
     pkg = graft.load_package()
     if world > 1:
         from caps_sa_b200 import multi_gpu  # sharded path (torch.distributed plumbing + our kernels)
-        out = multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks, NCU_TRAFFIC_RATIO)
+        out = multi_gpu.bench_main(args, spec, n, pkg, make_text, ClockSampler, load_peaks, KernelClassTimes)
         dist.barrier()
         dist.destroy_process_group()
         if out is not None:  # rank 0: check the assembled result of the last end-to-end step, then report
@@ -280,16 +339,14 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
-    scatter_ms, scatter_launches, scatter_bytes = 0.0, 0, 0
+    kernel_times = KernelClassTimes()
     stage_ms = {}
     ev0.record(stream)
     for _ in range(args.steps):
         device_step()
         st = eng.stats()
         launches += st["kernel_launches"]
-        scatter_ms += st["ms_scatter"]
-        scatter_launches += st["scatter_launches"]
-        scatter_bytes += st["scatter_bytes"]
+        kernel_times.add(st)
         for k in ("ms_pack", "ms_sort", "ms_heads", "ms_refine", "ms_deep_lcp", "ms_total"):
             stage_ms[k] = stage_ms.get(k, 0.0) + st[k] / args.steps
     ev1.record(stream)
@@ -329,19 +386,9 @@ def main():
         verified = verify_result(text_np, sa_host, lcp_host)
 
     peak, peak_kind = load_peaks()
-    achieved = (scatter_bytes / 1e9) / (scatter_ms / 1e3) if scatter_ms > 0 else None
-    roofline = {
-        "kernel": "radix_scatter_kernel", "bound": "hbm",
-        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "peak_source": peak_kind,
-        "traffic": NCU_TRAFFIC_RATIO * scatter_bytes / max(1, scatter_launches),
-        "traffic_source": "ncu --set full capture of this kernel (profiles/r01/scatter_ncu_full_v4.csv): dram read + "
-                          f"write = {NCU_TRAFFIC_RATIO:.3f} x algorithmic bytes, scaled to this run's mean launch",
-        "launches_timed": scatter_launches, "avg_launch_ms": scatter_ms / max(1, scatter_launches),
-        "share_of_step": scatter_ms / args.steps / dev_ms,
-        "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches),
-        "pipeline_frac": (n * 9 / 1e9) / (dev_ms / 1e3) / peak,  # 9 B/suffix compulsory traffic
-    }
+    roofline, kernel_table = kernel_times.report(peak, peak_kind, args.steps, dev_ms)
+    if roofline is not None:
+        roofline["pipeline_frac"] = (n * 9 / 1e9) / (dev_ms / 1e3) / peak  # 9 B/suffix compulsory traffic
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -360,13 +407,16 @@ def main():
         "config": {"workload": f"{args.workload}: {spec['desc']}", "n": n, "idx_bytes": 4,
                    "bits_per_symbol": last_stats["bits_per_symbol"], "l2": "inputs >> 126 MB L2, no explicit flush",
                    "text_generation_s": round(gen_s, 1), "tied_after_key_sort": last_stats["tied_after_key_sort"],
-                   "refine_rounds": last_stats["refine_rounds"]},
+                   "refine_rounds": last_stats["refine_rounds"],
+                   "key_sort": (f"packed-record MSD sort, {last_stats['msd_a_bits']} + {last_stats['msd_b_bits']} bits then one CTA per bucket; "
+                                f"{last_stats['msd_large_buckets']} oversized buckets ({last_stats['msd_large_records']} records) by the LSD passes"
+                                if last_stats["msd_a_bits"] else "LSD passes")},
         "e2e": {"value": n / (e2e_ms / 1e3), "unit": "suffixes/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": n, "d2h_bytes_per_step": 2 * 4 * n, "matches_device_result": same},
         "verified": verified,
         "gpu_launches": int(launches),
         "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "roofline": roofline, "kernels": kernel_table, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if (verified and verified["code"] != 0) or same is False:

@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "caps_sa_gpu_construct_multi_u32", "caps_sa_gpu_construct_multi_u64", "caps_sa_gpu_comm_unique_id",
     "caps_sa_gpu_engine_comm_init", "caps_sa_gpu_construct_sharded_device_u32",
     "caps_sa_gpu_construct_sharded_device_u64", "caps_sa_gpu_construct_sharded_u32",
-    "caps_sa_gpu_construct_sharded_u64", "caps_sa_gpu_shard_copy",
+    "caps_sa_gpu_construct_sharded_u64", "caps_sa_gpu_shard_copy", "caps_sa_gpu_stage_key_sort_u32",
 ]
 COMM_ID_BYTES = 128
 
@@ -51,7 +51,15 @@ class Stats(C.Structure):
                 ("ms_scatter", C.c_float), ("scatter_bytes", C.c_uint64), ("key_bits", C.c_uint32),
                 ("reserved", C.c_uint32), ("ms_partition", C.c_float), ("ms_merge", C.c_float),
                 ("comm_bytes", C.c_uint64), ("shard_offset", C.c_uint64), ("shard_count", C.c_uint64),
-                ("pairs_chained", C.c_uint64)]
+                ("pairs_chained", C.c_uint64),
+                ("msd_a_bits", C.c_uint32), ("msd_b_bits", C.c_uint32), ("msd_large_buckets", C.c_uint32),
+                ("msd_reserved", C.c_uint32), ("msd_large_records", C.c_uint64),
+                ("ms_msd_scatter_a", C.c_float), ("ms_msd_scatter_b", C.c_float), ("ms_msd_local", C.c_float),
+                ("ms_msd_hist", C.c_float),
+                ("msd_scatter_a_bytes", C.c_uint64), ("msd_scatter_b_bytes", C.c_uint64),
+                ("msd_local_bytes", C.c_uint64), ("msd_hist_bytes", C.c_uint64),
+                ("msd_scatter_a_launches", C.c_uint32), ("msd_scatter_b_launches", C.c_uint32),
+                ("msd_local_launches", C.c_uint32), ("msd_hist_launches", C.c_uint32)]
 
     def as_dict(self) -> dict:
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -93,6 +101,7 @@ def lib():
         L.caps_sa_gpu_stage_pack.argtypes = [p, p, u64, p, C.POINTER(u64), C.POINTER(u32)]
         L.caps_sa_gpu_stage_radix_sort_u64_u32.argtypes = [p, p, p, u64, C.c_uint, C.c_uint]
         L.caps_sa_gpu_stage_scan_u32.argtypes = [p, p, u64, i32]
+        L.caps_sa_gpu_stage_key_sort_u32.argtypes = [p, p, u64, i32, p, p]
         for name in ("caps_sa_gpu_construct_multi_u32", "caps_sa_gpu_construct_multi_u64"):
             getattr(L, name).argtypes = [C.POINTER(i32), i32, p, u64, p, p, u64, u64, C.POINTER(Stats)]
         L.caps_sa_gpu_comm_unique_id.argtypes = [p]
@@ -233,6 +242,19 @@ class Engine:
         _check(lib().caps_sa_gpu_stage_radix_sort_u64_u32(self._h, keys.ctypes.data, vals.ctypes.data,
                                                           len(keys), begin_bit, end_bit))
         return keys, vals
+
+    def stage_key_sort(self, text: np.ndarray, use_lsd: bool = False):
+        """(key_bits, keys, sa): all suffixes of `text` ordered by their leading key_bits key bits
+        (keys left-aligned in 64 bits); equal keys in no particular order."""
+        assert text.dtype == np.uint8 and text.flags.c_contiguous
+        n = len(text)
+        keys = np.empty(n, dtype=np.uint64)
+        sa = np.empty(n, dtype=np.uint32)
+        bits = lib().caps_sa_gpu_stage_key_sort_u32(self._h, text.ctypes.data, n, int(use_lsd), keys.ctypes.data,
+                                                    sa.ctypes.data)
+        if bits < 0:
+            _check(-bits)
+        return bits, keys, sa
 
     def stage_scan(self, data: np.ndarray, inclusive_max: bool) -> np.ndarray:
         data = np.ascontiguousarray(data, dtype=np.uint32).copy()

@@ -182,6 +182,16 @@ void fill_stats(const capsb::Stats& s, caps_sa_gpu_stats* out) {
   out->comm_bytes = s.comm_bytes;
   out->shard_offset = s.shard_offset, out->shard_count = s.shard_count;
   out->pairs_chained = s.pairs_chained;
+  out->msd_a_bits = s.msd_a_bits, out->msd_b_bits = s.msd_b_bits;
+  out->msd_large_buckets = s.msd_large_buckets;
+  out->msd_reserved = 0;
+  out->msd_large_records = s.msd_large_records;
+  out->ms_msd_scatter_a = s.ms_msd_scatter_a, out->ms_msd_scatter_b = s.ms_msd_scatter_b;
+  out->ms_msd_local = s.ms_msd_local, out->ms_msd_hist = s.ms_msd_hist;
+  out->msd_scatter_a_bytes = s.msd_scatter_a_bytes, out->msd_scatter_b_bytes = s.msd_scatter_b_bytes;
+  out->msd_local_bytes = s.msd_local_bytes, out->msd_hist_bytes = s.msd_hist_bytes;
+  out->msd_scatter_a_launches = s.msd_scatter_a_launches, out->msd_scatter_b_launches = s.msd_scatter_b_launches;
+  out->msd_local_launches = s.msd_local_launches, out->msd_hist_launches = s.msd_hist_launches;
 }
 
 template <class IdxT>
@@ -351,6 +361,7 @@ int caps_sa_gpu_engine_set_stream(caps_sa_gpu_engine* engine, void* stream) {
 int caps_sa_gpu_engine_set_kernel_timing(caps_sa_gpu_engine* engine, int enabled) {
   if (!engine) return bad_args("engine is NULL");
   engine->impl.radix.timer.enabled = enabled != 0;
+  engine->impl.msd_timers.set_enabled(enabled != 0);
   return CAPS_SA_GPU_OK;
 }
 
@@ -515,6 +526,30 @@ int caps_sa_gpu_stage_radix_sort_u64_u32(caps_sa_gpu_engine* engine, uint64_t* k
     CAPSB_CUDA(cudaStreamSynchronize(st));
     return CAPS_SA_GPU_OK;
   });
+}
+
+int caps_sa_gpu_stage_key_sort_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n, int use_lsd,
+                                   uint64_t* keys_out, uint32_t* sa_out) {
+  if (!engine || (n && (!text || !keys_out || !sa_out))) return -bad_args("NULL argument");
+  if (n > 0xFFFFFFFFull) return -bad_args("n does not fit 32-bit indices");
+  int key_bits = 0;
+  const int rc = guarded([&]() -> int {
+    Engine& eng = engine->impl;
+    capsb::ArenaScope arena_scope(&eng.arena);
+    CAPSB_CUDA(cudaSetDevice(eng.dev.device));
+    if (n == 0) return CAPS_SA_GPU_OK;
+    cudaStream_t st = eng.stream;
+    capsb::DevBuf<uint8_t> d_text(n, st);
+    capsb::DevBuf<uint64_t> d_keys(n, st);
+    capsb::DevBuf<uint32_t> d_sa(n, st);
+    CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
+    key_bits = capsb::stage_key_sort_u32(eng, d_text.get(), n, use_lsd != 0, d_keys.get(), d_sa.get());
+    CAPSB_CUDA(cudaMemcpyAsync(keys_out, d_keys.get(), n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaMemcpyAsync(sa_out, d_sa.get(), n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    return CAPS_SA_GPU_OK;
+  });
+  return rc == CAPS_SA_GPU_OK ? key_bits : -rc;
 }
 
 int caps_sa_gpu_stage_scan_u32(caps_sa_gpu_engine* engine, uint32_t* data, uint64_t n, int inclusive_max) {

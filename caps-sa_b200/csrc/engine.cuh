@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "packed_text.cuh"
 #include "radix_sort.cuh"
+#include "msd_sort.cuh"
 
 namespace capsb {
 
@@ -30,6 +31,13 @@ struct Stats {
   float ms_scatter = 0;
   uint64_t scatter_bytes = 0;
   uint32_t key_bits = 0;  // leading bits of the packed prefix the key sort used
+  // packed-record MSD sort (msd_sort.cuh): digit widths, per-kernel-class times and algorithmic bytes
+  uint32_t msd_a_bits = 0, msd_b_bits = 0;
+  uint32_t msd_large_buckets = 0;  // buckets that fell back to the LSD sort
+  uint64_t msd_large_records = 0;
+  float ms_msd_scatter_a = 0, ms_msd_scatter_b = 0, ms_msd_local = 0, ms_msd_hist = 0;
+  uint64_t msd_scatter_a_bytes = 0, msd_scatter_b_bytes = 0, msd_local_bytes = 0, msd_hist_bytes = 0;
+  uint32_t msd_scatter_a_launches = 0, msd_scatter_b_launches = 0, msd_local_launches = 0, msd_hist_launches = 0;
   // sharded construction only
   float ms_partition = 0;     // pivots, pivot location and the (key, suffix) all-to-all
   float ms_merge = 0;         // merge-path tree over the received runs
@@ -62,6 +70,7 @@ struct Engine {
   cudaStream_t stream = nullptr;      // stream all work is issued on
   cudaStream_t own_stream = nullptr;  // created with the engine
   RadixScratch radix;
+  MsdTimers msd_timers;
   ScanScratch<uint32_t> scan32;
   ScanScratch<uint64_t> scan64;
   Stats stats;
@@ -106,6 +115,21 @@ struct StreamScope {
 PackedTextBuf pack_text(Engine& eng, const uint8_t* d_text, uint64_t n);
 void map_acgt_device(Engine& eng, uint8_t* d_text, uint64_t n);
 
+// Moves the per-kernel-class timings of the last construction into eng.stats (after the stream has
+// been synchronised).
+inline void collect_msd_timings(Engine& eng) {
+  MsdTimers& t = eng.msd_timers;
+  if (!t.enabled) return;
+  eng.stats.msd_scatter_a_bytes = t.scatter_a.bytes;
+  eng.stats.ms_msd_scatter_a = t.scatter_a.drain(&eng.stats.msd_scatter_a_launches);
+  eng.stats.msd_scatter_b_bytes = t.scatter_b.bytes;
+  eng.stats.ms_msd_scatter_b = t.scatter_b.drain(&eng.stats.msd_scatter_b_launches);
+  eng.stats.msd_local_bytes = t.local.bytes;
+  eng.stats.ms_msd_local = t.local.drain(&eng.stats.msd_local_launches);
+  eng.stats.msd_hist_bytes = t.hist.bytes;
+  eng.stats.ms_msd_hist = t.hist.drain(&eng.stats.msd_hist_launches);
+}
+
 // sa_build.cu — the construction path (reference construct(), src/Suffix_Array.cpp:466-494)
 template <class IdxT>
 void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, IdxT* d_lcp);
@@ -113,6 +137,10 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
 // sharded_build.cu — the same path with one rank per GPU; collective over the ranks of `comm`
 template <class IdxT>
 void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64_t n, ShardResult<IdxT>& out);
+
+// Test hook: the key sort of all suffixes (packed-record MSD sort, or the LSD passes when use_lsd);
+// returns the key width.  Fills the sort-related statistics.
+int stage_key_sort_u32(Engine& eng, const uint8_t* d_text, uint64_t n, bool use_lsd, uint64_t* d_keys, uint32_t* d_sa);
 
 // Test hook: the two scan flavours the pipeline uses (inclusive max, exclusive sum).
 void stage_scan_u32(Engine& eng, const uint32_t* d_in, uint32_t* d_out, uint64_t n, bool inclusive_max);

@@ -1,0 +1,715 @@
+// Key sort of suffixes, most significant digit first, on packed 8-byte records — the sort the
+// single-GPU path and every rank's bucket sort use for 32-bit indices (replaces permute +
+// sort_subarrays / merge_sort, reference src/Suffix_Array.cpp:112-184).
+//
+// Why not the LSD sort of radix_sort.cuh: its passes carry (u64 key, u32 suffix) pairs, five
+// times through HBM for a 40-bit key, and each pass is bound by the SM's shared-memory pipe, not
+// by HBM (profiles/r01).  Here a suffix is ONE 64-bit record, (remaining key bits << 32) | suffix:
+// digits already consumed are implied by where the record lies, so they are dropped.
+//
+//   level A   the suffixes are partitioned by the top `a` bits of their key, read straight from
+//             the packed text; nothing but the 8-byte records is written;
+//   level B   every level-A bucket is partitioned by the next `b` bits: 2^(a+b) buckets of a few
+//             thousand records each (a + b is chosen from the number of suffixes);
+//   local     one CTA per bucket: the bucket is loaded into shared memory, ordered by the
+//             remaining bits (one counting pass on their top bits, then each small group is ordered
+//             by comparison, larger groups by one more counting pass), and leaves as the sorted
+//             keys — written in place of the records — plus the suffix array.
+// Three trips through HBM instead of five, 16 B per record and trip instead of 24.  A partition
+// need not be stable (whatever order equal digits come in, the next level sorts them), so a
+// record's rank inside its tile is ONE shared-memory atomicAdd on a per-CTA counter instead of
+// the per-warp match masks, leader counters and three table look-ups of the stable LSD pass.
+// Buckets too large for shared memory (texts dominated by one key: periodic, all-equal) fall
+// back to the LSD sort over just those buckets.
+#pragma once
+
+#include "radix_sort.cuh"
+
+namespace capsb {
+
+#ifndef CAPSB_MSD_THREADS  // tools/msd_bench.cu builds other layouts for A/B runs
+#define CAPSB_MSD_THREADS 512
+#endif
+#ifndef CAPSB_MSD_ITEMS
+#define CAPSB_MSD_ITEMS 12
+#endif
+#ifndef CAPSB_MSD_MIN_CTAS
+#define CAPSB_MSD_MIN_CTAS 2
+#endif
+constexpr int kMsdThreads = CAPSB_MSD_THREADS;
+constexpr int kMsdItems = CAPSB_MSD_ITEMS;
+constexpr int kMsdTile = kMsdThreads * kMsdItems;  // 6144 records = 48 KB
+constexpr int kMsdMaxBits = 10;                    // digit width of levels A and B
+constexpr int kMsdMaxBins = 1 << kMsdMaxBits;
+constexpr int kMsdLocalBits = 12;                  // digit width of the counting passes inside a bucket
+constexpr int kMsdLocalBins = 1 << kMsdLocalBits;
+constexpr int kMsdLocalCap = kMsdTile;             // largest bucket the local sort takes
+constexpr unsigned kMsdSmallGroup = 32;            // groups up to this size are ordered by comparison
+static_assert(kMsdTile <= 8192 && kMsdThreads % 32 == 0, "ranks are packed in 13 / 16 bits");
+
+// A piece = the part of one parent bucket that one CTA partitions: records [begin, end).
+struct MsdPiece {
+  uint32_t parent, begin, end, reserved;
+};
+
+// ---- sources -----------------------------------------------------------------------------
+// load(pos, rec, d): the record of input position pos and its digit at this level.
+struct MsdRecordSource {
+  const uint64_t* in;
+  unsigned shift, mask;
+  __device__ __forceinline__ void load(uint64_t pos, uint64_t& rec, unsigned& d) const {
+    rec = ld_stream_u64(in + pos);
+    d = static_cast<unsigned>(rec >> shift) & mask;
+  }
+  __device__ __forceinline__ unsigned digit_of(uint64_t rec) const { return static_cast<unsigned>(rec >> shift) & mask; }
+};
+
+// Level A: the key comes from the first-pass source of the LSD sort (TextSource: window of the
+// packed text at suffix base + pos; SuffixListSource: window at suffix idx[pos]); the digit is
+// its top bits and does not travel with the record.
+template <class First>
+struct MsdFirstSource {
+  First first;
+  unsigned key_shift;  // 64 - key_bits
+  unsigned rem_bits;   // key_bits - a
+  __device__ __forceinline__ void load(uint64_t pos, uint64_t& rec, unsigned& d) const {
+    const uint64_t k = first.key(pos) >> key_shift;
+    d = static_cast<unsigned>(k >> rem_bits);
+    rec = ((k & ((1ull << rem_bits) - 1ull)) << 32) | static_cast<uint64_t>(first.val(pos));
+  }
+  __device__ __forceinline__ unsigned digit_of(uint64_t) const { return 0; }  // not recoverable: kDigitInRec = false
+};
+
+// ---- block-wide exclusive sum ------------------------------------------------------------
+// One value per thread; warp_tot[32] is scratch (the caller separates consecutive uses by a
+// barrier).  Contains one __syncthreads.
+template <int kThreads>
+__device__ __forceinline__ unsigned msd_block_excl_scan(unsigned v, unsigned* warp_tot, unsigned* total = nullptr) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  unsigned inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned o = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= static_cast<unsigned>(d)) inc += o;
+  }
+  if (lane == 31u) warp_tot[warp] = inc;
+  __syncthreads();
+  unsigned prefix = 0, all = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const unsigned t = warp_tot[w];
+    if (static_cast<unsigned>(w) < warp) prefix += t;
+    all += t;
+  }
+  if (total) *total = all;
+  return prefix + inc - v;
+}
+
+// Rank of a record among the records of its digit counted so far in this tile: normally one
+// shared-memory atomicAdd.  When a probe row finds the warp's digits heavily repeated (texts
+// dominated by one symbol), the lanes that share a digit elect a leader that adds their number
+// once — same-address atomics of one warp instruction would serialise.  d == bins marks a lane
+// without a record (its count goes to the spare counter).  Warp-uniform `aggregate`.
+__device__ __forceinline__ unsigned msd_count(unsigned* cnt, unsigned d, bool has, bool aggregate, unsigned lane,
+                                              unsigned lt) {
+  if (!aggregate) return has ? atomicAdd(&cnt[d], 1u) : 0u;
+  const unsigned peers = __match_any_sync(0xffffffffu, d);
+  const int leader = __ffs(static_cast<int>(peers)) - 1;
+  unsigned base = 0;
+  if (static_cast<int>(lane) == leader) base = atomicAdd(&cnt[d], static_cast<unsigned>(__popc(peers)));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + static_cast<unsigned>(__popc(peers & lt));
+}
+__device__ __forceinline__ bool msd_probe(unsigned d, bool has) {
+  const unsigned peers = __match_any_sync(0xffffffffu, has ? d : 0xffffffffu);
+  return __any_sync(0xffffffffu, has && __popc(peers) >= 8);
+}
+
+// ---- planning: parents -> pieces ---------------------------------------------------------
+// One CTA.  Parent x (records [parent_start[x], parent_start[x+1])) is cut into
+// ceil(size / target) pieces of equal length (a multiple of the tile); piece_first[x] is its
+// first piece, piece_first[nparents] = *piece_count the number of pieces.
+static __global__ void __launch_bounds__(1024) msd_plan_kernel(const uint32_t* __restrict__ parent_start,
+                                                               unsigned nparents, uint32_t target,
+                                                               MsdPiece* __restrict__ pieces,
+                                                               uint32_t* __restrict__ piece_first,
+                                                               uint32_t* __restrict__ piece_count) {
+  __shared__ unsigned warp_tot[32];
+  const unsigned x = threadIdx.x;
+  uint32_t begin = 0, size = 0;
+  if (x < nparents) {
+    begin = parent_start[x];
+    size = parent_start[x + 1] - begin;
+  }
+  const uint32_t np = size ? (size - 1) / target + 1 : 0;
+  unsigned total;
+  const unsigned first = msd_block_excl_scan<1024>(np, warp_tot, &total);
+  if (x < nparents) piece_first[x] = first;
+  if (x == 0) {
+    piece_first[nparents] = total;
+    *piece_count = total;
+  }
+  if (np) {
+    uint64_t per = (static_cast<uint64_t>(size) + np - 1) / np;
+    per = (per + kMsdTile - 1) / kMsdTile * kMsdTile;
+    const uint64_t stop = static_cast<uint64_t>(begin) + size;
+    for (uint32_t j = 0; j < np; ++j) {
+      uint64_t b = begin + j * per, e = b + per;
+      if (b > stop) b = stop;
+      if (e > stop) e = stop;
+      pieces[first + j] = MsdPiece{x, static_cast<uint32_t>(b), static_cast<uint32_t>(e), 0u};
+    }
+  }
+}
+
+// ---- histogram of one piece --------------------------------------------------------------
+template <class Src>
+__global__ void __launch_bounds__(kMsdThreads) msd_hist_kernel(Src src, const MsdPiece* __restrict__ pieces,
+                                                               const uint32_t* __restrict__ piece_count, unsigned bins,
+                                                               uint32_t* __restrict__ hist) {
+  __shared__ unsigned cnt[kMsdMaxBins + 1];
+  if (blockIdx.x >= *piece_count) return;
+  const MsdPiece pc = pieces[blockIdx.x];
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const unsigned lt = lanemask_lt();
+  for (unsigned b = tid; b <= bins; b += kMsdThreads) cnt[b] = 0;
+  __syncthreads();
+  for (uint64_t tile = pc.begin; tile < pc.end; tile += kMsdTile) {
+    const unsigned valid = static_cast<unsigned>(pc.end - tile < kMsdTile ? pc.end - tile : kMsdTile);
+    unsigned d[kMsdItems];
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      uint64_t rec;
+      d[t] = bins;
+      if (e < valid) src.load(tile + e, rec, d[t]);
+    }
+    const bool aggregate = msd_probe(d[0], d[0] != bins);
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      if (!aggregate) {
+        if (d[t] != bins) atomicAdd(&cnt[d[t]], 1u);
+      } else {
+        const unsigned peers = __match_any_sync(0xffffffffu, d[t]);
+        if (static_cast<int>(lane) == __ffs(static_cast<int>(peers)) - 1)
+          atomicAdd(&cnt[d[t]], static_cast<unsigned>(__popc(peers)));
+      }
+    }
+    (void)lt;
+  }
+  __syncthreads();
+  for (unsigned b = tid; b < bins; b += kMsdThreads) hist[static_cast<uint64_t>(blockIdx.x) * bins + b] = cnt[b];
+}
+
+// ---- offsets -----------------------------------------------------------------------------
+// One CTA per parent, one thread per bin.  In: hist[piece][bin] = counts.  Out, in place:
+// hist[piece][bin] = where the piece's records of that bin go; child_start[parent * bins + bin]
+// = start of the child bucket (the children of a parent tile it in bin order), and one closing
+// entry child_start[nparents * bins] = end of the last parent.
+static __global__ void __launch_bounds__(kMsdMaxBins) msd_offsets_kernel(const uint32_t* __restrict__ parent_start,
+                                                                         unsigned nparents,
+                                                                         const uint32_t* __restrict__ piece_first,
+                                                                         unsigned bins, uint32_t* __restrict__ hist,
+                                                                         uint32_t* __restrict__ child_start) {
+  __shared__ unsigned warp_tot[32];
+  const unsigned x = blockIdx.x, b = threadIdx.x;
+  const uint32_t p0 = piece_first[x], p1 = piece_first[x + 1];
+  const bool live = b < bins;
+  uint32_t tot = 0;
+  if (live) {
+    uint32_t p = p0;
+    for (; p + 8 <= p1; p += 8) {  // eight independent loads in flight
+      uint32_t v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = hist[static_cast<uint64_t>(p + q) * bins + b];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) tot += v[q];
+    }
+    for (; p < p1; ++p) tot += hist[static_cast<uint64_t>(p) * bins + b];
+  }
+  const unsigned excl = msd_block_excl_scan<kMsdMaxBins>(tot, warp_tot);
+  if (!live) return;
+  const uint32_t base = parent_start[x] + excl;
+  child_start[static_cast<uint64_t>(x) * bins + b] = base;
+  if (x + 1 == nparents && b + 1 == bins) child_start[static_cast<uint64_t>(nparents) * bins] = parent_start[nparents];
+  uint32_t run = base;
+  uint32_t p = p0;
+  for (; p + 8 <= p1; p += 8) {
+    uint32_t v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = hist[static_cast<uint64_t>(p + q) * bins + b];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      hist[static_cast<uint64_t>(p + q) * bins + b] = run;
+      run += v[q];
+    }
+  }
+  for (; p < p1; ++p) {
+    const uint32_t v = hist[static_cast<uint64_t>(p) * bins + b];
+    hist[static_cast<uint64_t>(p) * bins + b] = run;
+    run += v;
+  }
+}
+
+// ---- partition of one piece --------------------------------------------------------------
+// Per tile of 8192 records: every thread loads 16 records (coalesced), takes their ranks with
+// one shared-memory atomicAdd each, the 512 threads scan the <= 1024 counters, the records go
+// to their place in the staging area (sorted by digit), and consecutive threads write
+// consecutive staged records: only whole digit runs leave the SM.  Four barriers per tile.
+template <bool kDigitInRec>
+struct MsdScatterSmem {
+  uint64_t stage[kMsdTile];
+  unsigned cnt[kMsdMaxBins + 1];  // [bins] collects the lanes without a record
+  unsigned start[kMsdMaxBins];    // first staged slot of each digit in this tile
+  unsigned gout[kMsdMaxBins];     // next free output slot of each digit for this piece
+  unsigned shiftv[kMsdMaxBins];   // output slot of staged slot s is shiftv[digit] + s (mod 2^32)
+  unsigned warp_tot[32];
+  uint16_t sdig[kDigitInRec ? 2 : kMsdTile];  // digit of each staged record when the record does not hold it
+};
+
+template <class Src, bool kDigitInRec>
+__global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_scatter_kernel(Src src, const MsdPiece* __restrict__ pieces,
+                                                                     const uint32_t* __restrict__ piece_count,
+                                                                     unsigned bins, const uint32_t* __restrict__ off,
+                                                                     uint64_t* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char msd_smem_raw[];
+  MsdScatterSmem<kDigitInRec>& sm = *reinterpret_cast<MsdScatterSmem<kDigitInRec>*>(msd_smem_raw);
+  if (blockIdx.x >= *piece_count) return;
+  const MsdPiece pc = pieces[blockIdx.x];
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const unsigned lt = lanemask_lt();
+  for (unsigned b = tid; b < bins; b += kMsdThreads) {
+    sm.gout[b] = off[static_cast<uint64_t>(blockIdx.x) * bins + b];
+    sm.cnt[b] = 0;
+  }
+  if (tid == 0) sm.cnt[bins] = 0;
+  __syncthreads();
+  for (uint64_t tile = pc.begin; tile < pc.end; tile += kMsdTile) {
+    const unsigned valid = static_cast<unsigned>(pc.end - tile < kMsdTile ? pc.end - tile : kMsdTile);
+    uint64_t rec[kMsdItems];
+    // rank of every record inside its digit (< 8192).  With the digit in the record two ranks share
+    // a register (the digit is recomputed); otherwise the digit rides along (digit | rank << 11).
+    unsigned dr[kDigitInRec ? kMsdItems / 2 : kMsdItems];
+    unsigned probe_d = bins;
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      rec[t] = 0;
+      unsigned d = bins;
+      if (e < valid) src.load(tile + e, rec[t], d);
+      if (t == 0) probe_d = d;
+      if (!kDigitInRec) dr[t] = d;
+    }
+    const bool aggregate = msd_probe(probe_d, probe_d != bins);
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      if constexpr (kDigitInRec) {
+        const unsigned d = e < valid ? src.digit_of(rec[t]) : bins;
+        const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
+        if (t & 1)
+          dr[t >> 1] |= r << 16;
+        else
+          dr[t >> 1] = r;
+      } else {
+        const unsigned d = dr[t];
+        const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
+        dr[t] = d | (r << 11);
+      }
+    }
+    __syncthreads();
+    {  // consecutive digits per thread: starts inside the tile, output shifts; counters back to zero
+      constexpr int kPer = (kMsdMaxBins + kMsdThreads - 1) / kMsdThreads;
+      unsigned c[kPer], sum = 0;
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const unsigned b = tid * kPer + q;
+        c[q] = b < bins ? sm.cnt[b] : 0u;
+        sum += c[q];
+      }
+      unsigned run = msd_block_excl_scan<kMsdThreads>(sum, sm.warp_tot);
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const unsigned b = tid * kPer + q;
+        if (b < bins) {
+          const unsigned g = sm.gout[b];
+          sm.start[b] = run;
+          sm.shiftv[b] = g - run;
+          sm.gout[b] = g + c[q];
+          sm.cnt[b] = 0;
+        }
+        run += c[q];
+      }
+      if (tid == 0) sm.cnt[bins] = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      if (e < valid) {
+        unsigned d, r;
+        if constexpr (kDigitInRec) {
+          d = src.digit_of(rec[t]);
+          r = (dr[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
+        } else {
+          d = dr[t] & 0x7FFu;
+          r = dr[t] >> 11;
+        }
+        const unsigned slot = sm.start[d] + r;
+        sm.stage[slot] = rec[t];
+        if (!kDigitInRec) sm.sdig[slot] = static_cast<uint16_t>(d);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned s = static_cast<unsigned>(t) * kMsdThreads + tid;
+      if (s < valid) {
+        const uint64_t r = sm.stage[s];
+        const unsigned d = kDigitInRec ? src.digit_of(r) : static_cast<unsigned>(sm.sdig[s]);
+        out[static_cast<uint32_t>(sm.shiftv[d] + s)] = r;
+      }
+    }
+    // no barrier here: the next tile touches the staging area and the tables only after its own
+    // first barrier, which every thread reaches after it has finished these stores
+  }
+}
+
+// ---- local sort: one CTA per bucket ------------------------------------------------------
+// Bucket q = records [child_start[q], child_start[q+1]) of `recs`, all with the same leading
+// prefix_bits = a + b key bits (= q); the remaining rem_bits sit at bits [32, 32 + rem_bits) of
+// the record.  On return the same slots hold the sorted keys (key_bits bits, left-aligned, the
+// form the rest of the pipeline uses) and sa_out the suffixes.  Buckets larger than the shared
+// memory staging area are left alone and appended to large_list.
+struct MsdLocalSmem {
+  uint64_t stage[kMsdLocalCap];
+  unsigned cnt[kMsdLocalBins + 1];
+  unsigned start[kMsdLocalBins + 1];
+  unsigned warp_tot[32];
+  unsigned big[kMsdLocalCap / (kMsdSmallGroup + 1) + 1];  // digits of the groups too large for comparison ordering
+  unsigned nbig;
+};
+
+// Counting pass over records held in registers (rec[t] for the elements e = t * threads + tid <
+// count of the range [base, base + count) of the staging area): ranks, scan of `bins` counters
+// (bins <= 4096), records written back sorted by the digit at `shift`.  start[] holds the digit
+// starts (relative to base) afterwards, start[bins] = count.  All threads of the CTA call it.
+__device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)[kMsdItems], unsigned base,
+                                               unsigned count, unsigned shift, unsigned bits) {
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const unsigned lt = lanemask_lt();
+  const unsigned bins = 1u << bits, mask = bins - 1u;
+  unsigned rk[kMsdItems / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
+  const bool has0 = tid < count;
+  const bool aggregate = msd_probe(has0 ? (static_cast<unsigned>(rec[0] >> shift) & mask) : bins, has0);
+#pragma unroll
+  for (int t = 0; t < kMsdItems; ++t) {
+    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
+    const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
+    if (t & 1)
+      rk[t >> 1] |= r << 16;
+    else
+      rk[t >> 1] = r;
+  }
+  __syncthreads();
+  {  // consecutive counters per thread (512 x 8 = 4096)
+    constexpr int kPer = (kMsdLocalBins + kMsdThreads - 1) / kMsdThreads;
+    unsigned c[kPer], sum = 0;
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const unsigned b = tid * kPer + q;
+      c[q] = b < bins ? sm.cnt[b] : 0u;
+      sum += c[q];
+    }
+    unsigned run = msd_block_excl_scan<kMsdThreads>(sum, sm.warp_tot);
+#pragma unroll
+    for (int q = 0; q < kPer; ++q) {
+      const unsigned b = tid * kPer + q;
+      if (b < bins) {
+        sm.start[b] = run;
+        sm.cnt[b] = 0;
+      }
+      run += c[q];
+    }
+    if (tid == 0) {
+      sm.start[bins] = count;
+      sm.cnt[bins] = 0;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < kMsdItems; ++t) {
+    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    if (e < count) {
+      const unsigned d = static_cast<unsigned>(rec[t] >> shift) & mask;
+      sm.stage[base + sm.start[d] + ((rk[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu)] = rec[t];
+    }
+  }
+  __syncthreads();
+}
+
+static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_local_kernel(uint64_t* __restrict__ recs,
+                                                                  const uint32_t* __restrict__ child_start,
+                                                                  uint32_t nbuckets, unsigned key_bits,
+                                                                  unsigned prefix_bits, uint32_t* __restrict__ sa_out,
+                                                                  uint32_t* __restrict__ large_list,
+                                                                  uint32_t* __restrict__ large_count) {
+  extern __shared__ __align__(16) unsigned char msd_smem_raw[];
+  MsdLocalSmem& sm = *reinterpret_cast<MsdLocalSmem*>(msd_smem_raw);
+  const unsigned tid = threadIdx.x;
+  const unsigned rem_bits = key_bits - prefix_bits;  // <= 24
+  const unsigned hb = rem_bits < static_cast<unsigned>(kMsdLocalBits) ? rem_bits : static_cast<unsigned>(kMsdLocalBits);
+  const unsigned lb = rem_bits - hb;                 // <= 12
+  const unsigned key_shift = 64u - key_bits;
+  for (unsigned b = tid; b <= static_cast<unsigned>(kMsdLocalBins); b += kMsdThreads) sm.cnt[b] = 0;
+  if (tid == 0) sm.nbig = 0;
+  __syncthreads();
+  for (uint32_t q = blockIdx.x; q < nbuckets; q += gridDim.x) {
+    const uint32_t beg = child_start[q];
+    const uint32_t count = child_start[q + 1] - beg;
+    if (count == 0) continue;
+    if (count > static_cast<uint32_t>(kMsdLocalCap)) {
+      if (tid == 0) large_list[atomicAdd(large_count, 1u)] = q;
+      continue;
+    }
+    // the key bits every record of this bucket shares, in place above the remaining ones
+    const uint64_t prefix = static_cast<uint64_t>(q) << rem_bits;
+    const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
+    uint64_t rec[kMsdItems];
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      rec[t] = e < count ? ld_stream_u64(recs + beg + e) : 0ull;
+    }
+    if (hb > 0 && count > 1) {
+      msd_local_pass(sm, rec, 0, count, 32u + lb, hb);
+      if (lb == 0) {  // the pass consumed every remaining bit
+        for (unsigned s = tid; s < count; s += kMsdThreads) {
+          const uint64_t r = sm.stage[s];
+          recs[beg + s] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
+          sa_out[beg + s] = static_cast<uint32_t>(r);
+        }
+      } else {
+        // groups = runs of equal top digits, now contiguous.  A record of a small group counts the
+        // records of its group that precede it (by the remaining bits, then by slot) and leaves
+        // for its final place at once: key in place of the records, suffix to the suffix array.
+        // Large groups are listed and get a counting pass of their own.
+        const unsigned hmask = (1u << hb) - 1u;
+#pragma unroll 4
+        for (unsigned s = tid; s < count; s += kMsdThreads) {
+          const uint64_t r = sm.stage[s];
+          const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
+          const unsigned g0 = sm.start[d], g1 = sm.start[d + 1];
+          if (g1 - g0 <= kMsdSmallGroup) {
+            const unsigned mine = static_cast<unsigned>(r >> 32);
+            unsigned rank = 0;
+            for (unsigned u = g0; u < g1; ++u) {
+              const unsigned other = static_cast<unsigned>(sm.stage[u] >> 32);
+              rank += (other < mine || (other == mine && u < s)) ? 1u : 0u;
+            }
+            recs[beg + g0 + rank] = (prefix | (static_cast<uint64_t>(mine) & rem_mask)) << key_shift;
+            sa_out[beg + g0 + rank] = static_cast<uint32_t>(r);
+          } else if (s == g0) {
+            sm.big[atomicAdd(&sm.nbig, 1u)] = g0 | ((g1 - g0 - 1u) << 16);  // start, size - 1 < 65536
+          }
+        }
+        __syncthreads();
+        const unsigned nbig = sm.nbig;
+        for (unsigned j = 0; j < nbig; ++j) {
+          const unsigned g0 = sm.big[j] & 0xFFFFu, gsize = (sm.big[j] >> 16) + 1u;
+#pragma unroll
+          for (int t = 0; t < kMsdItems; ++t) {
+            const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+            rec[t] = e < gsize ? sm.stage[g0 + e] : 0ull;
+          }
+          __syncthreads();  // every record of the group is in registers before any is written back
+          msd_local_pass(sm, rec, g0, gsize, 32u, lb);
+          for (unsigned e = tid; e < gsize; e += kMsdThreads) {
+            const uint64_t r = sm.stage[g0 + e];
+            recs[beg + g0 + e] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
+            sa_out[beg + g0 + e] = static_cast<uint32_t>(r);
+          }
+        }
+        if (nbig > 0) {
+          __syncthreads();
+          if (tid == 0) sm.nbig = 0;
+        }
+      }
+      __syncthreads();  // the staging area is refilled by the next bucket
+    } else {
+#pragma unroll
+      for (int t = 0; t < kMsdItems; ++t) {
+        const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+        if (e < count) {
+          recs[beg + e] = (prefix | ((rec[t] >> 32) & rem_mask)) << key_shift;
+          sa_out[beg + e] = static_cast<uint32_t>(rec[t]);
+        }
+      }
+    }
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------
+struct MsdPlan {
+  unsigned a = 0, b = 0;  // digit widths of levels A and B
+};
+
+inline unsigned msd_ceil_log2(uint64_t v) {
+  unsigned b = 0;
+  while ((1ull << b) < v) ++b;
+  return b;
+}
+inline unsigned round_up8_bits(unsigned b) { return b == 0 ? 8u : (b + 7u) & ~7u; }
+
+// Can the packed-record sort take this job?  The key must leave room for a 32-bit suffix next
+// to its remaining bits after level A (a <= 10), and the buckets' remaining bits must fit the two
+// counting passes of the local sort.
+inline bool msd_applicable(unsigned key_bits) { return key_bits >= 16 && key_bits <= 32u + kMsdMaxBits; }
+
+inline MsdPlan msd_plan(uint64_t count, unsigned key_bits) {
+  // about 2048 records per bucket; at least key_bits - 24 leading bits so that the local sort's
+  // two passes (12 + 12) cover the rest
+  unsigned p = msd_ceil_log2((count + 2047) / 2048);
+  if (p < 2) p = 2;
+  if (key_bits > 24 && p < key_bits - 24) p = key_bits - 24;
+  if (p > 2 * kMsdMaxBits) p = 2 * kMsdMaxBits;
+  MsdPlan plan;
+  plan.a = (p + 1) / 2;
+  if (key_bits > 32 && plan.a < key_bits - 32) plan.a = key_bits - 32;
+  plan.b = p > plan.a ? p - plan.a : 1;
+  if (plan.b > static_cast<unsigned>(kMsdMaxBits)) plan.b = kMsdMaxBits;
+  return plan;
+}
+
+// Per-kernel-class CUDA-event timing (bench.py's roofline figures), same scheme as KernelTimer.
+struct MsdTimers {
+  bool enabled = false;
+  KernelTimer scatter_a, scatter_b, local, hist;
+  void reset() { scatter_a.reset(), scatter_b.reset(), local.reset(), hist.reset(); }
+  void set_enabled(bool on) { enabled = scatter_a.enabled = scatter_b.enabled = local.enabled = hist.enabled = on; }
+};
+
+struct MsdTimed {
+  KernelTimer& timer;
+  cudaStream_t stream;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  MsdTimed(KernelTimer& t, cudaStream_t st, uint64_t bytes) : timer(t), stream(st) {
+    if (!timer.enabled) return;
+    t0 = timer.get();
+    t1 = timer.get();
+    timer.bytes += bytes;
+    cudaEventRecord(t0, stream);
+  }
+  ~MsdTimed() {
+    if (!timer.enabled) return;
+    cudaEventRecord(t1, stream);
+    timer.pending.emplace_back(t0, t1);
+  }
+};
+
+template <class Kernel>
+inline void msd_allow_smem(Kernel kernel, size_t bytes) {
+  // per call: the attribute belongs to the current context (one per device), and the call costs
+  // a few hundred nanoseconds
+  CAPSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+}
+
+// One partition level: the records of `parents` (nparents + 1 starts on the device) are
+// partitioned by the digit `src` yields into `bins` children each; child_start gets
+// nparents * bins + 1 entries.
+template <class Src, bool kDigitInRec>
+inline void msd_partition_level(const DeviceInfo& dev, cudaStream_t st, MsdTimers& timers, KernelTimer& scatter_timer,
+                                Src src, uint64_t count, const uint32_t* parent_start, unsigned nparents,
+                                unsigned bits, unsigned pieces_per_sm, uint64_t in_bytes_per_record,
+                                uint32_t* child_start, uint64_t* out) {
+  const unsigned bins = 1u << bits;
+  const uint64_t want_pieces = static_cast<uint64_t>(dev.sm_count) * pieces_per_sm;
+  uint64_t target = (count + want_pieces - 1) / want_pieces;
+  target = (target + kMsdTile - 1) / kMsdTile * kMsdTile;
+  const unsigned max_pieces = static_cast<unsigned>(count / target + nparents + 1);
+  DevBuf<MsdPiece> pieces(max_pieces, st);
+  DevBuf<uint32_t> piece_first(nparents + 1, st), piece_count(1, st);
+  DevBuf<uint32_t> hist(static_cast<uint64_t>(max_pieces) * bins, st);
+  CAPSB_LAUNCH(msd_plan_kernel, 1, 1024, 0, st, parent_start, nparents, static_cast<uint32_t>(target), pieces.get(),
+               piece_first.get(), piece_count.get());
+  {
+    MsdTimed timed(timers.hist, st, count * in_bytes_per_record);
+    CAPSB_LAUNCH((msd_hist_kernel<Src>), max_pieces, kMsdThreads, 0, st, src, pieces.get(), piece_count.get(), bins,
+                 hist.get());
+  }
+  CAPSB_LAUNCH(msd_offsets_kernel, nparents, kMsdMaxBins, 0, st, parent_start, nparents, piece_first.get(), bins,
+               hist.get(), child_start);
+  {
+    constexpr size_t kSmem = sizeof(MsdScatterSmem<kDigitInRec>);
+    msd_allow_smem(msd_scatter_kernel<Src, kDigitInRec>, kSmem);
+    MsdTimed timed(scatter_timer, st, count * (in_bytes_per_record + sizeof(uint64_t)));
+    CAPSB_LAUNCH((msd_scatter_kernel<Src, kDigitInRec>), max_pieces, kMsdThreads, kSmem, st, src, pieces.get(),
+                 piece_count.get(), bins, hist.get(), out);
+  }
+}
+
+// The buckets the local sort could not take (more than kMsdLocalCap records): their records are
+// gathered, sorted by (bucket, remaining key bits) with the LSD sort, and written back as keys
+// and suffixes.
+inline void msd_sort_large_buckets(const DeviceInfo& dev, cudaStream_t st, RadixScratch& radix, uint64_t* recs,
+                                   uint32_t* sa_out, const uint32_t* child_start, const uint32_t* large_list,
+                                   uint32_t nlarge, unsigned key_bits, unsigned prefix_bits,
+                                   ScanScratch<uint32_t>& scan, uint64_t* records_out) {
+  const unsigned rem_bits = key_bits - prefix_bits;
+  DevBuf<uint32_t> loff(nlarge + 1, st);
+  uint32_t total = 0;
+  {
+    uint32_t* lo = loff.get();
+    device_scan<uint32_t, OpSum, false>(
+        dev, st, scan, nlarge,
+        [=] __device__(uint64_t j) -> uint32_t { return child_start[large_list[j] + 1] - child_start[large_list[j]]; },
+        [=] __device__(uint64_t j, uint32_t v) { lo[j] = v; }, &total);
+    launch_map(dev, st, 1, [=] __device__(uint64_t) { lo[nlarge] = total; });
+  }
+  if (records_out) *records_out = total;
+  DevBuf<uint64_t> key_a(total, st), key_b(total, st);
+  DevBuf<uint32_t> val_a(total, st), val_b(total, st);
+  const uint32_t* lo = loff.get();
+  auto bucket_of = [=] __device__(uint64_t e) -> uint32_t {  // last j with loff[j] <= e
+    uint32_t a = 0, b = nlarge;
+    while (b - a > 1) {
+      const uint32_t mid = (a + b) >> 1;
+      if (lo[mid] <= e)
+        a = mid;
+      else
+        b = mid;
+    }
+    return a;
+  };
+  {
+    uint64_t* ka = key_a.get();
+    uint32_t* va = val_a.get();
+    const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
+    launch_map(dev, st, total, [=] __device__(uint64_t e) {
+      const uint32_t j = bucket_of(e);
+      const uint64_t r = recs[child_start[large_list[j]] + (e - lo[j])];
+      ka[e] = (static_cast<uint64_t>(j) << rem_bits) | ((r >> 32) & rem_mask);
+      va[e] = static_cast<uint32_t>(r);
+    });
+  }
+  const unsigned sort_bits = round_up8_bits(rem_bits + msd_ceil_log2(nlarge));
+  const int where = radix_sort_pairs<uint64_t, uint32_t>(st, radix, key_a.get(), val_a.get(), key_b.get(), val_b.get(),
+                                                        total, 0, sort_bits);
+  {
+    const uint64_t* ks = where ? key_b.get() : key_a.get();
+    const uint32_t* vs = where ? val_b.get() : val_a.get();
+    const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
+    const unsigned key_shift = 64u - key_bits;
+    launch_map(dev, st, total, [=] __device__(uint64_t e) {
+      const uint64_t k = ks[e];
+      const uint32_t j = static_cast<uint32_t>(k >> rem_bits);
+      const uint32_t q = large_list[j];
+      const uint64_t pos = child_start[q] + (e - lo[j]);
+      recs[pos] = ((static_cast<uint64_t>(q) << rem_bits) | (k & rem_mask)) << key_shift;
+      sa_out[pos] = vs[e];
+    });
+  }
+}
+
+}  // namespace capsb

@@ -19,6 +19,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <type_traits>
 
 #include "engine.cuh"
@@ -169,10 +170,68 @@ void scan_full(Engine& eng, uint64_t n, In in, Out out) {
 // Key sort of the suffixes [base, base + count): on return keys_out / sa_out hold them in key
 // order (keys masked to key_bits).  keys_out and sa_out are caller-owned, `count` entries.
 // ---------------------------------------------------------------------------------------
+// CAPSB_SORT=lsd keeps the key sort on the LSD passes of radix_sort.cuh (read per construction:
+// the tests flip it); default is the packed-record MSD sort where it applies.
+inline bool msd_sort_enabled() {
+  const char* env = std::getenv("CAPSB_SORT");
+  return !(env && std::string(env) == "lsd");
+}
+
+// The packed-record MSD sort (msd_sort.cuh) of `count` suffixes given by `first` (key(i) = masked
+// text window of the i-th suffix, val(i) = the suffix).  keys_out doubles as the level-B record
+// buffer: the local sort turns it into the sorted keys in place.
+template <class FirstSrc>
+void msd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
+                       uint32_t* sa_out) {
+  cudaStream_t st = eng.stream;
+  const DeviceInfo& dev = eng.dev;
+  const MsdPlan plan = msd_plan(count, key_bits);
+  const unsigned a = plan.a, b = plan.b;
+  const unsigned rem_a = key_bits - a;  // <= 32: the record's key field after level A
+  eng.stats.msd_a_bits = a;
+  eng.stats.msd_b_bits = b;
+  const uint32_t nbuckets = 1u << (a + b);
+  DevBuf<uint32_t> root(2, st), start_a((1u << a) + 1, st), start_b(static_cast<uint64_t>(nbuckets) + 1, st);
+  {
+    uint32_t* r = root.get();
+    const uint32_t c = static_cast<uint32_t>(count);
+    launch_map(dev, st, 1, [=] __device__(uint64_t) { r[0] = 0, r[1] = c; });
+  }
+  {
+    DevBuf<uint64_t> rec_a(count, st);
+    // level A: digit = top a bits of the key, records = (remaining bits << 32) | suffix
+    msd_partition_level<MsdFirstSource<FirstSrc>, false>(
+        dev, st, eng.msd_timers, eng.msd_timers.scatter_a, MsdFirstSource<FirstSrc>{first, 64u - key_bits, rem_a},
+        count, root.get(), 1, a, 2, FirstSrc::bytes_read_per_item(), start_a.get(), rec_a.get());
+    // level B: every level-A bucket by the next b bits
+    msd_partition_level<MsdRecordSource, true>(dev, st, eng.msd_timers, eng.msd_timers.scatter_b,
+                                               MsdRecordSource{rec_a.get(), 32u + rem_a - b, (1u << b) - 1u}, count,
+                                               start_a.get(), 1u << a, b, 8, sizeof(uint64_t), start_b.get(),
+                                               keys_out);
+  }
+  // local sort of every bucket; the oversized ones are listed
+  DevBuf<uint32_t> large_list(count / kMsdLocalCap + 1, st), large_count(1, st);
+  CAPSB_CUDA(cudaMemsetAsync(large_count.get(), 0, sizeof(uint32_t), st));
+  {
+    constexpr size_t kSmem = sizeof(MsdLocalSmem);
+    msd_allow_smem(msd_local_kernel, kSmem);
+    const uint32_t grid = std::min<uint32_t>(nbuckets, static_cast<uint32_t>(dev.sm_count) * 2u);
+    MsdTimed timed(eng.msd_timers.local, st, count * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
+    CAPSB_LAUNCH(msd_local_kernel, grid, kMsdThreads, kSmem, st, keys_out, start_b.get(), nbuckets, key_bits, a + b,
+                 sa_out, large_list.get(), large_count.get());
+  }
+  uint32_t nlarge = 0;
+  read_back(st, &nlarge, large_count.get(), sizeof(uint32_t));
+  eng.stats.msd_large_buckets = nlarge;
+  if (nlarge > 0)
+    msd_sort_large_buckets(dev, st, eng.radix, keys_out, sa_out, start_b.get(), large_list.get(), nlarge, key_bits,
+                           a + b, eng.scan32, &eng.stats.msd_large_records);
+}
+
+// The LSD sort: stable 8-bit passes over (u64 key, suffix) pairs, the first one reading the keys
+// from `first` (64-bit indices, keys too wide for the packed records, CAPSB_SORT=lsd).
 template <class IdxT, class FirstSrc>
-void sort_suffixes_by_key(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
-                          IdxT* sa_out) {
-  if (count == 0) return;
+void lsd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out, IdxT* sa_out) {
   cudaStream_t st = eng.stream;
   const unsigned passes = key_bits / 8;
   DevBuf<uint64_t> key_tmp(count, st);
@@ -189,6 +248,19 @@ void sort_suffixes_by_key(Engine& eng, FirstSrc first, uint64_t count, unsigned 
     radix_pass<uint64_t, IdxT>(st, eng.radix, ArraySource<uint64_t, IdxT>{key_buf[in], val_buf[in]}, count,
                                64 - key_bits + 8 * q, key_buf[out], val_buf[out]);
   }
+}
+
+template <class IdxT, class FirstSrc>
+void sort_suffixes_by_key(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
+                          IdxT* sa_out) {
+  if (count == 0) return;
+  if constexpr (sizeof(IdxT) == 4) {
+    if (msd_sort_enabled() && msd_applicable(key_bits) && count <= 0xFFFFFFFFull) {
+      msd_sort_suffixes(eng, first, count, key_bits, keys_out, sa_out);
+      return;
+    }
+  }
+  lsd_sort_suffixes<IdxT>(eng, first, count, key_bits, keys_out, sa_out);
 }
 
 // The suffixes [base, base + count) of the text.

@@ -73,6 +73,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   const uint64_t launches_before = g_kernel_launches.load();
   eng.stats = Stats();
   eng.radix.timer.reset();
+  eng.msd_timers.reset();
   eng.stats.n = n;
   eng.stats.idx_bytes = sizeof(IdxT);
   if (n == 0) return;
@@ -148,6 +149,34 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     eng.stats.scatter_bytes = eng.radix.timer.bytes;
     eng.stats.ms_scatter = eng.radix.timer.drain(&eng.stats.scatter_launches);
   }
+  collect_msd_timings(eng);
+}
+
+int stage_key_sort_u32(Engine& eng, const uint8_t* d_text, uint64_t n, bool use_lsd, uint64_t* d_keys, uint32_t* d_sa) {
+  eng.stats = Stats();
+  eng.radix.timer.reset();
+  eng.msd_timers.reset();
+  PackedTextBuf packed = pack_text(eng, d_text, n);
+  const PackedText pt = packed.view(n);
+  const unsigned key_bits = choose_key_bits(n);
+  const TextSource<uint32_t> first{pt, key_mask_of(key_bits), 0};
+  StageClock clock(eng);
+  clock.mark();
+  if (use_lsd || !msd_applicable(key_bits))
+    lsd_sort_suffixes<uint32_t>(eng, first, n, key_bits, d_keys, d_sa);
+  else
+    msd_sort_suffixes(eng, first, n, key_bits, d_keys, d_sa);
+  clock.mark();
+  CAPSB_CUDA(cudaStreamSynchronize(eng.stream));
+  eng.stats.n = n;
+  eng.stats.key_bits = key_bits;
+  eng.stats.ms_sort = clock.between(0, 1);
+  if (eng.radix.timer.enabled) {
+    eng.stats.scatter_bytes = eng.radix.timer.bytes;
+    eng.stats.ms_scatter = eng.radix.timer.drain(&eng.stats.scatter_launches);
+  }
+  collect_msd_timings(eng);
+  return static_cast<int>(key_bits);
 }
 
 void stage_scan_u32(Engine& eng, const uint32_t* d_in, uint32_t* d_out, uint64_t n, bool inclusive_max) {

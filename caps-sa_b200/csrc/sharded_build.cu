@@ -377,6 +377,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   const uint64_t comm_bytes_before = comm.bytes_sent;
   eng.stats = Stats();
   eng.radix.timer.reset();
+  eng.msd_timers.reset();
   eng.stats.n = n;
   eng.stats.idx_bytes = sizeof(IdxT);
   out.offset = out.count = 0;
@@ -693,6 +694,7 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
     eng.stats.scatter_bytes = eng.radix.timer.bytes;
     eng.stats.ms_scatter = eng.radix.timer.drain(&eng.stats.scatter_launches);
   }
+  collect_msd_timings(eng);
 }
 
 template void build_sa_lcp_sharded<uint32_t>(Engine&, Comm&, const uint8_t*, uint64_t, ShardResult<uint32_t>&);

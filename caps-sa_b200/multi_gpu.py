@@ -150,7 +150,7 @@ def bind_to_gpu_cpus(device_index: int):
 
 
 # ---- bench.py, N > 1 -----------------------------------------------------------------------
-def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, traffic_ratio=None):
+def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, kernel_times_cls):
     """bench.py's multi-rank arm: same JSON contract, time = max over ranks, value = n / time.
     The text is fixed (strong scaling): every rank generates the same synthetic text.
     Returns (json line, (text, SA, LCP) host arrays) on rank 0, None on the other ranks."""
@@ -229,19 +229,16 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, tra
         sampler.start()
     launches = 0.0
     comm_bytes = 0.0
-    scatter_ms = scatter_bytes = 0.0
-    scatter_launches = 0
+    kernel_times = kernel_times_cls()
     stage_ms = {}
 
     def counted_step():
-        nonlocal launches, comm_bytes, scatter_ms, scatter_bytes, scatter_launches
+        nonlocal launches, comm_bytes
         device_step()
         st = seng.stats()
         launches += st["kernel_launches"]
         comm_bytes += st["comm_bytes"]
-        scatter_ms += st["ms_scatter"]
-        scatter_bytes += st["scatter_bytes"]
-        scatter_launches += st["scatter_launches"]
+        kernel_times.add(st)
         for k in ("ms_pack", "ms_sort", "ms_partition", "ms_merge", "ms_refine", "ms_deep_lcp", "ms_total"):
             stage_ms[k] = stage_ms.get(k, 0.0) + st[k] / args.steps
 
@@ -271,7 +268,9 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, tra
     if rank != 0:
         return None
     peak, peak_kind = load_peaks()
-    achieved = (scatter_bytes / 1e9) / (scatter_ms / 1e3) if scatter_ms > 0 else None
+    roofline, kernel_table = kernel_times.report(peak, peak_kind, args.steps, dev_ms)
+    if roofline is not None:
+        roofline["kernel"] += " (rank 0)"
     line = {
         "metric": "sa_lcp_suffixes_per_sec", "value": n / (dev_ms / 1e3), "unit": "suffixes/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms,
@@ -287,14 +286,7 @@ def bench_main(args, spec, n, pkg, make_text, clock_sampler_cls, load_peaks, tra
         "gpu_launches": int(total_launches),
         "nvlink_bytes_per_step": total_comm / args.steps,
         "stage_ms_rank0": {k: round(v, 3) for k, v in stage_ms.items()},
-        "roofline": {"kernel": "radix_scatter_kernel (rank 0)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_kind,
-                     "traffic": (traffic_ratio * scatter_bytes / max(1, scatter_launches)) if traffic_ratio else None,
-                     "traffic_source": "ncu --set full capture of this kernel on one GPU (profiles/r01/scatter_ncu_full_v4.csv), "
-                                       "scaled to this run's mean launch",
-                     "launches_timed": scatter_launches,
-                     "avg_launch_ms": scatter_ms / max(1, scatter_launches),
-                     "algorithmic_bytes_per_launch": scatter_bytes / max(1, scatter_launches)},
+        "roofline": roofline, "kernels_rank0": kernel_table,
         "cpu_baseline": None, "clocks": clocks,
     }
     # rank 0 verifies the arrays all ranks wrote into the shared host buffers and prints the line

@@ -62,6 +62,18 @@ typedef struct caps_sa_gpu_stats {
   uint64_t shard_offset;        /* this rank owns SA/LCP positions [shard_offset, shard_offset + shard_count) */
   uint64_t shard_count;
   uint64_t pairs_chained;       /* groups of two suffixes finished by the pair-chain step (order + LCP) */
+  /* Key sort on packed 8-byte records, most significant digit first (32-bit indices): level A
+   * partitions the suffixes by the top msd_a_bits of their key straight from the text, level B every
+   * level-A bucket by the next msd_b_bits, the local sort orders each bucket in shared memory.
+   * Per kernel class, with kernel timing enabled: summed launch durations, algorithmic bytes
+   * (bytes each record is read and written with, once per launch) and launch counts. */
+  uint32_t msd_a_bits, msd_b_bits;
+  uint32_t msd_large_buckets;   /* buckets too large for shared memory, sorted by the LSD passes instead */
+  uint32_t msd_reserved;
+  uint64_t msd_large_records;
+  float ms_msd_scatter_a, ms_msd_scatter_b, ms_msd_local, ms_msd_hist;
+  uint64_t msd_scatter_a_bytes, msd_scatter_b_bytes, msd_local_bytes, msd_hist_bytes;
+  uint32_t msd_scatter_a_launches, msd_scatter_b_launches, msd_local_launches, msd_hist_launches;
 } caps_sa_gpu_stats;
 
 /* Number of CUDA devices visible to the library (0 if none / driver missing). */
@@ -179,6 +191,14 @@ int caps_sa_gpu_stage_pack(caps_sa_gpu_engine* engine, const char* text, uint64_
 /* Stable LSD radix sort of (keys, vals) on key bits [begin_bit, end_bit), in place. */
 int caps_sa_gpu_stage_radix_sort_u64_u32(caps_sa_gpu_engine* engine, uint64_t* keys, uint32_t* vals,
                                          uint64_t n, unsigned begin_bit, unsigned end_bit);
+
+/* Key sort of all suffixes of `text` (the stage that replaces permute + sort_subarrays, reference
+ * src/Suffix_Array.cpp:148-184): keys_out[k] = the leading key bits of suffix sa_out[k] (left-aligned
+ * in 64 bits, the rest zero), ascending; suffixes with equal keys come in no particular order.
+ * use_lsd != 0 forces the LSD passes of the 64-bit-index path.  Returns the key width in bits, or a
+ * negative error. */
+int caps_sa_gpu_stage_key_sort_u32(caps_sa_gpu_engine* engine, const char* text, uint64_t n, int use_lsd,
+                                   uint64_t* keys_out, uint32_t* sa_out);
 
 /* Inclusive max-scan and exclusive sum-scan of a uint32 array (the two scan flavours the
  * pipeline uses), in place. */

@@ -93,6 +93,60 @@ def test_stage_radix_sort_bit_range(engine):
     assert np.array_equal(gk, keys[order])
 
 
+def numpy_keys(text, positions, key_bits):
+    """Leading key_bits bits of the packed text at the given suffix positions, left-aligned in 64 bits."""
+    bits, words, _ = numpy_pack(text)
+    bitpos = positions.astype(np.uint64) * np.uint64(bits)
+    w = (bitpos >> np.uint64(6)).astype(np.int64)
+    off = bitpos & np.uint64(63)
+    hi = words[w] << off
+    lo = np.where(off == 0, np.uint64(0), words[w + 1] >> ((np.uint64(64) - off) & np.uint64(63)))
+    mask = np.uint64(((1 << key_bits) - 1) << (64 - key_bits))
+    return (hi | lo) & mask
+
+
+KEY_SORT_CASES = {
+    "acgt_1": lambda s: s.random_acgt(1, 1),
+    "acgt_2": lambda s: s.random_acgt(2, 1),
+    "acgt_100": lambda s: s.random_acgt(100, 2),
+    "acgt_6143": lambda s: s.random_acgt(6143, 3),
+    "acgt_6145": lambda s: s.random_acgt(6145, 3),
+    "acgt_70k": lambda s: s.random_acgt(70_001, 4),
+    "acgt_3M": lambda s: s.random_acgt(3_000_001, 5),
+    "acgt_20M": lambda s: s.random_acgt(20_000_000, 6),
+    "genome_like_5M": lambda s: s.genome_like(5_000_000, seed=7, scale=0.01),
+    "bytes256_1M": lambda s: s.random_bytes(1_000_000, 8),
+    "sigma3_2M": lambda s: s.random_bytes(2_000_000, 9, sigma=3, base=0xFE),
+    "allA_300k": lambda s: np.full(300_000, ord("A"), dtype=np.uint8),
+    "period3_500k": lambda s: s.periodic(500_000, b"ACG"),
+    "periodic_unit1000_2M": lambda s: s.periodic_random_unit(2_000_000, 1000, seed=4),
+    "fibonacci_1M": lambda s: s.fibonacci(1_000_000),
+    "polyA_runs_2M": lambda s: np.where(np.arange(2_000_000) % 50_000 < 30_000, ord("A"),
+                                        s.random_acgt(2_000_000, 10)).astype(np.uint8),
+}
+
+
+@pytest.mark.parametrize("use_lsd", [False, True])
+@pytest.mark.parametrize("case", sorted(KEY_SORT_CASES))
+def test_stage_key_sort(engine, synth, case, use_lsd):
+    """The key sort of all suffixes (packed-record MSD sort / LSD passes): a permutation of the
+    suffixes, keys ascending, every key the one of its suffix."""
+    text = KEY_SORT_CASES[case](synth)
+    n = len(text)
+    key_bits, keys, sa = engine.stage_key_sort(text, use_lsd=use_lsd)
+    assert key_bits % 8 == 0 and 16 <= key_bits <= 64
+    seen = np.zeros(n, dtype=bool)
+    seen[sa] = True
+    assert seen.all(), "not a permutation of the suffixes"
+    assert np.array_equal(keys, numpy_keys(text, sa, key_bits)), "a key does not belong to its suffix"
+    assert bool((keys[1:] >= keys[:-1]).all()), f"keys are not ascending ({engine.stats()})"
+    st = engine.stats()
+    if not use_lsd and key_bits <= 40:
+        assert st["msd_a_bits"] > 0
+        if case in ("allA_300k", "period3_500k", "polyA_runs_2M"):
+            assert st["msd_large_buckets"] > 0  # these exercise the oversized-bucket fallback
+
+
 @pytest.mark.parametrize("n", [1, 255, 2048, 2049, 1_000_003])
 def test_stage_scans(engine, n):
     rng = np.random.default_rng(n)
@@ -155,6 +209,18 @@ def test_matches_oracle(pkg, engine, synth, case):
     text, p = CASES[case](synth)
     want_sa, want_lcp = oracle_sa_lcp(text, p)
     sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
+    assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_matches_oracle_with_lsd_key_sort(pkg, engine, synth, case, monkeypatch):
+    """CAPSB_SORT=lsd: the key sort of the 64-bit-index path (stable LSD passes) under 32-bit indices."""
+    monkeypatch.setenv("CAPSB_SORT", "lsd")
+    text, p = CASES[case](synth)
+    want_sa, want_lcp = oracle_sa_lcp(text, p)
+    sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    assert stats["msd_a_bits"] == 0
     assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
     assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
 
