@@ -23,6 +23,7 @@
 // back to the LSD sort over just those buckets.
 #pragma once
 
+#include "packed_text.cuh"
 #include "radix_sort.cuh"
 
 namespace capsb {
@@ -53,16 +54,28 @@ struct MsdPiece {
 };
 
 // ---- sources -----------------------------------------------------------------------------
-// load(pos, rec, d): the record of input position pos and its digit at this level.
+// load_tile(tile, valid, bins, rec, d): this thread's kMsdItems records of the tile [tile, tile +
+// valid) and their digits at this level (d = bins where the thread has no record).  Which records
+// a thread takes is the source's choice — a partition need not be stable.
 struct MsdRecordSource {
   const uint64_t* in;
   unsigned shift, mask;
-  __device__ __forceinline__ void load(uint64_t pos, uint64_t& rec, unsigned& d) const {
-    rec = ld_stream_u64(in + pos);
-    d = static_cast<unsigned>(rec >> shift) & mask;
-  }
   __device__ __forceinline__ unsigned digit_of(uint64_t rec) const { return static_cast<unsigned>(rec >> shift) & mask; }
+  __device__ __forceinline__ void load_tile(uint64_t tile, unsigned valid, unsigned bins, uint64_t (&rec)[kMsdItems],
+                                            unsigned (&d)[kMsdItems]) const {
+#pragma unroll
+    for (int t = 0; t < kMsdItems; ++t) {  // striped: consecutive threads read consecutive records
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + threadIdx.x;
+      rec[t] = e < valid ? ld_stream_u64(in + tile + e) : 0ull;
+      d[t] = e < valid ? digit_of(rec[t]) : bins;
+    }
+  }
 };
+
+template <class First, class = void>
+struct MsdIsSequentialText : std::false_type {};
+template <class First>
+struct MsdIsSequentialText<First, std::enable_if_t<First::kSequentialText>> : std::true_type {};
 
 // Level A: the key comes from the first-pass source of the LSD sort (TextSource: window of the
 // packed text at suffix base + pos; SuffixListSource: window at suffix idx[pos]); the digit is
@@ -72,12 +85,50 @@ struct MsdFirstSource {
   First first;
   unsigned key_shift;  // 64 - key_bits
   unsigned rem_bits;   // key_bits - a
-  __device__ __forceinline__ void load(uint64_t pos, uint64_t& rec, unsigned& d) const {
-    const uint64_t k = first.key(pos) >> key_shift;
-    d = static_cast<unsigned>(k >> rem_bits);
-    rec = ((k & ((1ull << rem_bits) - 1ull)) << 32) | static_cast<uint64_t>(first.val(pos));
-  }
   __device__ __forceinline__ unsigned digit_of(uint64_t) const { return 0; }  // not recoverable: kDigitInRec = false
+  __device__ __forceinline__ void split(uint64_t key, uint64_t suffix, uint64_t& rec, unsigned& d) const {
+    const uint64_t k = key >> key_shift;
+    d = static_cast<unsigned>(k >> rem_bits);
+    rec = ((k & ((1ull << rem_bits) - 1ull)) << 32) | suffix;
+  }
+  __device__ __forceinline__ void load_tile(uint64_t tile, unsigned valid, unsigned bins, uint64_t (&rec)[kMsdItems],
+                                            unsigned (&d)[kMsdItems]) const {
+    if constexpr (MsdIsSequentialText<First>::value) {
+      // Consecutive suffixes of the text: the thread takes kMsdItems consecutive ones, loads the
+      // (at most four) packed words they span ONCE and shifts every window out of them — one
+      // wait on memory per tile instead of one per suffix.
+      const PackedText& pt = first.pt;
+      const unsigned e0 = threadIdx.x * kMsdItems;
+      const uint64_t p0 = first.base + tile + e0;
+      const unsigned bits = pt.bits();
+      const uint64_t bit0 = p0 << pt.log2_bits;
+      const uint64_t w0 = bit0 >> 6;
+      const uint64_t nwords = (((pt.n << pt.log2_bits) + 63) >> 6) + 2;
+      uint64_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) w[q] = (e0 < valid && w0 + q < nwords) ? __ldg(pt.words + w0 + q) : 0ull;
+      const unsigned o0 = static_cast<unsigned>(bit0 & 63u);
+#pragma unroll
+      for (int t = 0; t < kMsdItems; ++t) {
+        const unsigned o = o0 + static_cast<unsigned>(t) * bits;  // < 64 + 11 * 8 = 152
+        const unsigned q = o >> 6, r = o & 63u;
+        const uint64_t hi = q == 0 ? w[0] : (q == 1 ? w[1] : w[2]);
+        const uint64_t lo = q == 0 ? w[1] : (q == 1 ? w[2] : w[3]);
+        const uint64_t win = r ? (hi << r) | (lo >> (64u - r)) : hi;
+        rec[t] = 0;
+        d[t] = bins;
+        if (e0 + t < valid) split(win & first.mask, p0 + t, rec[t], d[t]);
+      }
+    } else {
+#pragma unroll
+      for (int t = 0; t < kMsdItems; ++t) {
+        const unsigned e = static_cast<unsigned>(t) * kMsdThreads + threadIdx.x;
+        rec[t] = 0;
+        d[t] = bins;
+        if (e < valid) split(first.key(tile + e), static_cast<uint64_t>(first.val(tile + e)), rec[t], d[t]);
+      }
+    }
+  }
 };
 
 // ---- block-wide exclusive sum ------------------------------------------------------------
@@ -163,6 +214,8 @@ static __global__ void __launch_bounds__(1024) msd_plan_kernel(const uint32_t* _
 }
 
 // ---- histogram of one piece --------------------------------------------------------------
+// gridDim.y CTAs share a piece (its tiles dealt round-robin) and add their counts into hist, which
+// the caller has zeroed.
 template <class Src>
 __global__ void __launch_bounds__(kMsdThreads) msd_hist_kernel(Src src, const MsdPiece* __restrict__ pieces,
                                                                const uint32_t* __restrict__ piece_count, unsigned bins,
@@ -171,19 +224,14 @@ __global__ void __launch_bounds__(kMsdThreads) msd_hist_kernel(Src src, const Ms
   if (blockIdx.x >= *piece_count) return;
   const MsdPiece pc = pieces[blockIdx.x];
   const unsigned tid = threadIdx.x, lane = tid & 31u;
-  const unsigned lt = lanemask_lt();
   for (unsigned b = tid; b <= bins; b += kMsdThreads) cnt[b] = 0;
   __syncthreads();
-  for (uint64_t tile = pc.begin; tile < pc.end; tile += kMsdTile) {
+  for (uint64_t tile = pc.begin + static_cast<uint64_t>(blockIdx.y) * kMsdTile; tile < pc.end;
+       tile += static_cast<uint64_t>(gridDim.y) * kMsdTile) {
     const unsigned valid = static_cast<unsigned>(pc.end - tile < kMsdTile ? pc.end - tile : kMsdTile);
+    uint64_t rec[kMsdItems];
     unsigned d[kMsdItems];
-#pragma unroll
-    for (int t = 0; t < kMsdItems; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-      uint64_t rec;
-      d[t] = bins;
-      if (e < valid) src.load(tile + e, rec, d[t]);
-    }
+    src.load_tile(tile, valid, bins, rec, d);
     const bool aggregate = msd_probe(d[0], d[0] != bins);
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {
@@ -195,10 +243,10 @@ __global__ void __launch_bounds__(kMsdThreads) msd_hist_kernel(Src src, const Ms
           atomicAdd(&cnt[d[t]], static_cast<unsigned>(__popc(peers)));
       }
     }
-    (void)lt;
   }
   __syncthreads();
-  for (unsigned b = tid; b < bins; b += kMsdThreads) hist[static_cast<uint64_t>(blockIdx.x) * bins + b] = cnt[b];
+  for (unsigned b = tid; b < bins; b += kMsdThreads)
+    if (cnt[b]) atomicAdd(&hist[static_cast<uint64_t>(blockIdx.x) * bins + b], cnt[b]);
 }
 
 // ---- offsets -----------------------------------------------------------------------------
@@ -252,18 +300,26 @@ static __global__ void __launch_bounds__(kMsdMaxBins) msd_offsets_kernel(const u
 }
 
 // ---- partition of one piece --------------------------------------------------------------
-// Per tile of 8192 records: every thread loads 16 records (coalesced), takes their ranks with
-// one shared-memory atomicAdd each, the 512 threads scan the <= 1024 counters, the records go
-// to their place in the staging area (sorted by digit), and consecutive threads write
-// consecutive staged records: only whole digit runs leave the SM.  Four barriers per tile.
+// Per tile: every thread takes kMsdItems records, ranks each with one shared-memory atomicAdd, the
+// threads scan the <= 1024 counters, the records go to their place in the staging area (sorted
+// by digit), and consecutive threads write consecutive staged records to the output.
+//
+// Only whole, aligned 32-byte sectors (four records) leave the SM.  With 1024 digits a tile holds
+// about six records per digit; writing such runs as they come leaves a partly written sector at
+// both ends of every run, and with a million runs open across the chip L2 evicts them before the
+// next tile completes them: 40 % more DRAM writes plus as many fill reads (ncu, profiles/r02).  So
+// a digit's records that do not fill a sector yet (at most three) are carried into the next tile,
+// where they head the digit's run; a tile takes fewer new records to make room for them.  The
+// piece's last tile writes everything.
 template <bool kDigitInRec>
 struct MsdScatterSmem {
   uint64_t stage[kMsdTile];
-  unsigned cnt[kMsdMaxBins + 1];  // [bins] collects the lanes without a record
-  unsigned start[kMsdMaxBins];    // first staged slot of each digit in this tile
-  unsigned gout[kMsdMaxBins];     // next free output slot of each digit for this piece
-  unsigned shiftv[kMsdMaxBins];   // output slot of staged slot s is shiftv[digit] + s (mod 2^32)
+  uint64_t carry[kMsdMaxBins * 3];  // the records carried over, three slots per digit
+  uint2 shlim[kMsdMaxBins];         // x: output slot of staged slot s is x + s (mod 2^32); y: staged slots below y leave now
+  unsigned cnt[kMsdMaxBins + 1];    // [bins] collects the lanes without a record; starts a tile at the digit's carried count
+  unsigned start[kMsdMaxBins];      // first staged slot of each digit in this tile
   unsigned warp_tot[32];
+  unsigned carried_next;            // records carried into the next tile (accumulated by the digit owners)
   uint16_t sdig[kDigitInRec ? 2 : kMsdTile];  // digit of each staged record when the record does not hold it
 };
 
@@ -278,48 +334,36 @@ __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_scatter_k
   const MsdPiece pc = pieces[blockIdx.x];
   const unsigned tid = threadIdx.x, lane = tid & 31u;
   const unsigned lt = lanemask_lt();
-  for (unsigned b = tid; b < bins; b += kMsdThreads) {
-    sm.gout[b] = off[static_cast<uint64_t>(blockIdx.x) * bins + b];
-    sm.cnt[b] = 0;
+  // this thread owns the digits tid * kPer .. + kPer - 1: their next output slot and carried count
+  constexpr int kPer = (kMsdMaxBins + kMsdThreads - 1) / kMsdThreads;
+  unsigned gout[kPer], kprev[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const unsigned b = tid * kPer + q;
+    gout[q] = b < bins ? off[static_cast<uint64_t>(blockIdx.x) * bins + b] : 0u;
+    kprev[q] = 0;
   }
-  if (tid == 0) sm.cnt[bins] = 0;
+  for (unsigned b = tid; b <= bins; b += kMsdThreads) sm.cnt[b] = 0;
+  if (tid == 0) sm.carried_next = 0;
   __syncthreads();
-  for (uint64_t tile = pc.begin; tile < pc.end; tile += kMsdTile) {
-    const unsigned valid = static_cast<unsigned>(pc.end - tile < kMsdTile ? pc.end - tile : kMsdTile);
+  unsigned carried = 0;
+  for (uint64_t pos = pc.begin; pos < pc.end;) {
+    const uint64_t left = pc.end - pos;
+    const unsigned room = kMsdTile - carried;
+    const unsigned valid = static_cast<unsigned>(left < room ? left : room);
+    const bool last = left <= room;
     uint64_t rec[kMsdItems];
-    // rank of every record inside its digit (< 8192).  With the digit in the record two ranks share
-    // a register (the digit is recomputed); otherwise the digit rides along (digit | rank << 11).
-    unsigned dr[kDigitInRec ? kMsdItems / 2 : kMsdItems];
-    unsigned probe_d = bins;
+    unsigned dr[kMsdItems];  // digit, then digit | rank << 11 (rank < 8192)
+    src.load_tile(pos, valid, bins, rec, dr);
+    const bool aggregate = msd_probe(dr[0], dr[0] != bins);
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-      rec[t] = 0;
-      unsigned d = bins;
-      if (e < valid) src.load(tile + e, rec[t], d);
-      if (t == 0) probe_d = d;
-      if (!kDigitInRec) dr[t] = d;
-    }
-    const bool aggregate = msd_probe(probe_d, probe_d != bins);
-#pragma unroll
-    for (int t = 0; t < kMsdItems; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-      if constexpr (kDigitInRec) {
-        const unsigned d = e < valid ? src.digit_of(rec[t]) : bins;
-        const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
-        if (t & 1)
-          dr[t >> 1] |= r << 16;
-        else
-          dr[t >> 1] = r;
-      } else {
-        const unsigned d = dr[t];
-        const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
-        dr[t] = d | (r << 11);
-      }
+      const unsigned d = dr[t];
+      const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
+      dr[t] = d | (r << 11);
     }
     __syncthreads();
-    {  // consecutive digits per thread: starts inside the tile, output shifts; counters back to zero
-      constexpr int kPer = (kMsdMaxBins + kMsdThreads - 1) / kMsdThreads;
+    {  // digit owners: starts inside the tile, what leaves now, what is carried, output shifts
       unsigned c[kPer], sum = 0;
 #pragma unroll
       for (int q = 0; q < kPer; ++q) {
@@ -328,50 +372,72 @@ __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_scatter_k
         sum += c[q];
       }
       unsigned run = msd_block_excl_scan<kMsdThreads>(sum, sm.warp_tot);
+      unsigned knew[kPer], ksum = 0;
 #pragma unroll
       for (int q = 0; q < kPer; ++q) {
         const unsigned b = tid * kPer + q;
+        knew[q] = 0;
         if (b < bins) {
-          const unsigned g = sm.gout[b];
+          const unsigned g = gout[q], e = g + c[q];
+          const unsigned aligned = e & ~3u;
+          // records beyond the last sector boundary wait (all of them if the run has not reached one)
+          const unsigned k = last ? 0u : e - (aligned > g ? aligned : g);
+          const unsigned f = c[q] - k;
           sm.start[b] = run;
-          sm.shiftv[b] = g - run;
-          sm.gout[b] = g + c[q];
-          sm.cnt[b] = 0;
+          sm.shlim[b] = make_uint2(g - run, run + f);
+          gout[q] = g + f;
+          sm.cnt[b] = k;
+          knew[q] = k;
+          ksum += k;
         }
         run += c[q];
       }
       if (tid == 0) sm.cnt[bins] = 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ksum += __shfl_xor_sync(0xffffffffu, ksum, o);
+      if (lane == 0 && ksum) atomicAdd(&sm.carried_next, ksum);
+      __syncthreads();
+      // the records carried in head their digit's run
+#pragma unroll
+      for (int q = 0; q < kPer; ++q) {
+        const unsigned b = tid * kPer + q;
+        for (unsigned j = 0; j < kprev[q]; ++j) {
+          const unsigned slot = sm.start[b] + j;
+          sm.stage[slot] = sm.carry[b * 3 + j];
+          if (!kDigitInRec) sm.sdig[slot] = static_cast<uint16_t>(b);
+        }
+        kprev[q] = knew[q];
+      }
     }
-    __syncthreads();
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-      if (e < valid) {
-        unsigned d, r;
-        if constexpr (kDigitInRec) {
-          d = src.digit_of(rec[t]);
-          r = (dr[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
-        } else {
-          d = dr[t] & 0x7FFu;
-          r = dr[t] >> 11;
-        }
-        const unsigned slot = sm.start[d] + r;
+      const unsigned d = dr[t] & 0x7FFu;
+      if (d != bins) {
+        const unsigned slot = sm.start[d] + (dr[t] >> 11);
         sm.stage[slot] = rec[t];
         if (!kDigitInRec) sm.sdig[slot] = static_cast<uint16_t>(d);
       }
     }
+    const unsigned total = valid + carried;
+    carried = sm.carried_next;
     __syncthreads();
+    if (tid == 0) sm.carried_next = 0;
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {
       const unsigned s = static_cast<unsigned>(t) * kMsdThreads + tid;
-      if (s < valid) {
+      if (s < total) {
         const uint64_t r = sm.stage[s];
         const unsigned d = kDigitInRec ? src.digit_of(r) : static_cast<unsigned>(sm.sdig[s]);
-        out[static_cast<uint32_t>(sm.shiftv[d] + s)] = r;
+        const uint2 sl = sm.shlim[d];
+        if (s < sl.y)
+          out[static_cast<uint32_t>(sl.x + s)] = r;
+        else
+          sm.carry[d * 3 + (s - sl.y)] = r;
       }
     }
-    // no barrier here: the next tile touches the staging area and the tables only after its own
-    // first barrier, which every thread reaches after it has finished these stores
+    pos += valid;
+    // no barrier here: the next tile touches the staging area, the tables and the carry slots only
+    // after its own first barrier, which every thread reaches after it has finished this loop
   }
 }
 
@@ -381,10 +447,16 @@ __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_scatter_k
 // the record.  On return the same slots hold the sorted keys (key_bits bits, left-aligned, the
 // form the rest of the pipeline uses) and sa_out the suffixes.  Buckets larger than the shared
 // memory staging area are left alone and appended to large_list.
+// Counter b lives at word b + (b >> 5): the scan's threads own eight consecutive counters each, and
+// the extra word per 32 spreads those stride-8 accesses over all banks (plain indexing: 8-way
+// conflicts, a third of the kernel's shared-memory traffic — ncu, profiles/r02).
+__device__ __forceinline__ unsigned msd_pad(unsigned b) { return b + (b >> 5); }
+constexpr int kMsdLocalPadded = kMsdLocalBins + kMsdLocalBins / 32 + 2;
+
 struct MsdLocalSmem {
   uint64_t stage[kMsdLocalCap];
-  unsigned cnt[kMsdLocalBins + 1];
-  unsigned start[kMsdLocalBins + 1];
+  unsigned cnt[kMsdLocalPadded];
+  unsigned start[kMsdLocalPadded];
   unsigned warp_tot[32];
   unsigned big[kMsdLocalCap / (kMsdSmallGroup + 1) + 1];  // digits of the groups too large for comparison ordering
   unsigned nbig;
@@ -399,27 +471,27 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
   const unsigned tid = threadIdx.x, lane = tid & 31u;
   const unsigned lt = lanemask_lt();
   const unsigned bins = 1u << bits, mask = bins - 1u;
-  unsigned rk[kMsdItems / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
+  unsigned rk[(kMsdItems + 1) / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
   const bool has0 = tid < count;
   const bool aggregate = msd_probe(has0 ? (static_cast<unsigned>(rec[0] >> shift) & mask) : bins, has0);
 #pragma unroll
   for (int t = 0; t < kMsdItems; ++t) {
     const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
     const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
-    const unsigned r = msd_count(sm.cnt, d, d != bins, aggregate, lane, lt);
+    const unsigned r = msd_count(sm.cnt, msd_pad(d), d != bins, aggregate, lane, lt);
     if (t & 1)
       rk[t >> 1] |= r << 16;
     else
       rk[t >> 1] = r;
   }
   __syncthreads();
-  {  // consecutive counters per thread (512 x 8 = 4096)
+  {  // eight consecutive counters per thread
     constexpr int kPer = (kMsdLocalBins + kMsdThreads - 1) / kMsdThreads;
     unsigned c[kPer], sum = 0;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
       const unsigned b = tid * kPer + q;
-      c[q] = b < bins ? sm.cnt[b] : 0u;
+      c[q] = b < bins ? sm.cnt[msd_pad(b)] : 0u;
       sum += c[q];
     }
     unsigned run = msd_block_excl_scan<kMsdThreads>(sum, sm.warp_tot);
@@ -427,14 +499,14 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
     for (int q = 0; q < kPer; ++q) {
       const unsigned b = tid * kPer + q;
       if (b < bins) {
-        sm.start[b] = run;
-        sm.cnt[b] = 0;
+        sm.start[msd_pad(b)] = run;
+        sm.cnt[msd_pad(b)] = 0;
       }
       run += c[q];
     }
     if (tid == 0) {
-      sm.start[bins] = count;
-      sm.cnt[bins] = 0;
+      sm.start[msd_pad(bins)] = count;
+      sm.cnt[msd_pad(bins)] = 0;
     }
   }
   __syncthreads();
@@ -443,7 +515,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
     const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
     if (e < count) {
       const unsigned d = static_cast<unsigned>(rec[t] >> shift) & mask;
-      sm.stage[base + sm.start[d] + ((rk[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu)] = rec[t];
+      sm.stage[base + sm.start[msd_pad(d)] + ((rk[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu)] = rec[t];
     }
   }
   __syncthreads();
@@ -459,10 +531,8 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
   MsdLocalSmem& sm = *reinterpret_cast<MsdLocalSmem*>(msd_smem_raw);
   const unsigned tid = threadIdx.x;
   const unsigned rem_bits = key_bits - prefix_bits;  // <= 24
-  const unsigned hb = rem_bits < static_cast<unsigned>(kMsdLocalBits) ? rem_bits : static_cast<unsigned>(kMsdLocalBits);
-  const unsigned lb = rem_bits - hb;                 // <= 12
   const unsigned key_shift = 64u - key_bits;
-  for (unsigned b = tid; b <= static_cast<unsigned>(kMsdLocalBins); b += kMsdThreads) sm.cnt[b] = 0;
+  for (unsigned b = tid; b < static_cast<unsigned>(kMsdLocalPadded); b += kMsdThreads) sm.cnt[b] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
   for (uint32_t q = blockIdx.x; q < nbuckets; q += gridDim.x) {
@@ -473,6 +543,15 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
       if (tid == 0) large_list[atomicAdd(large_count, 1u)] = q;
       continue;
     }
+    // The first counting pass takes the top hb of the remaining bits: about one counter per two
+    // records (the scan of the counters is per-bucket overhead), at least rem_bits - 12 so that
+    // one more pass can finish a large group, at most 12.
+    unsigned hb = 1;
+    while ((2u << hb) < count) ++hb;
+    if (hb > static_cast<unsigned>(kMsdLocalBits)) hb = kMsdLocalBits;
+    if (hb + kMsdLocalBits < rem_bits) hb = rem_bits - kMsdLocalBits;
+    if (hb > rem_bits) hb = rem_bits;
+    const unsigned lb = rem_bits - hb;
     // the key bits every record of this bucket shares, in place above the remaining ones
     const uint64_t prefix = static_cast<uint64_t>(q) << rem_bits;
     const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
@@ -500,7 +579,7 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
         for (unsigned s = tid; s < count; s += kMsdThreads) {
           const uint64_t r = sm.stage[s];
           const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
-          const unsigned g0 = sm.start[d], g1 = sm.start[d + 1];
+          const unsigned g0 = sm.start[msd_pad(d)], g1 = sm.start[msd_pad(d + 1)];
           if (g1 - g0 <= kMsdSmallGroup) {
             const unsigned mine = static_cast<unsigned>(r >> 32);
             unsigned rank = 0;
@@ -621,8 +700,8 @@ inline void msd_allow_smem(Kernel kernel, size_t bytes) {
 template <class Src, bool kDigitInRec>
 inline void msd_partition_level(const DeviceInfo& dev, cudaStream_t st, MsdTimers& timers, KernelTimer& scatter_timer,
                                 Src src, uint64_t count, const uint32_t* parent_start, unsigned nparents,
-                                unsigned bits, unsigned pieces_per_sm, uint64_t in_bytes_per_record,
-                                uint32_t* child_start, uint64_t* out) {
+                                unsigned bits, unsigned pieces_per_sm, unsigned hist_split,
+                                uint64_t in_bytes_per_record, uint32_t* child_start, uint64_t* out) {
   const unsigned bins = 1u << bits;
   const uint64_t want_pieces = static_cast<uint64_t>(dev.sm_count) * pieces_per_sm;
   uint64_t target = (count + want_pieces - 1) / want_pieces;
@@ -633,10 +712,11 @@ inline void msd_partition_level(const DeviceInfo& dev, cudaStream_t st, MsdTimer
   DevBuf<uint32_t> hist(static_cast<uint64_t>(max_pieces) * bins, st);
   CAPSB_LAUNCH(msd_plan_kernel, 1, 1024, 0, st, parent_start, nparents, static_cast<uint32_t>(target), pieces.get(),
                piece_first.get(), piece_count.get());
+  CAPSB_CUDA(cudaMemsetAsync(hist.get(), 0, static_cast<uint64_t>(max_pieces) * bins * sizeof(uint32_t), st));
   {
     MsdTimed timed(timers.hist, st, count * in_bytes_per_record);
-    CAPSB_LAUNCH((msd_hist_kernel<Src>), max_pieces, kMsdThreads, 0, st, src, pieces.get(), piece_count.get(), bins,
-                 hist.get());
+    CAPSB_LAUNCH((msd_hist_kernel<Src>), dim3(max_pieces, hist_split), kMsdThreads, 0, st, src, pieces.get(),
+                 piece_count.get(), bins, hist.get());
   }
   CAPSB_LAUNCH(msd_offsets_kernel, nparents, kMsdMaxBins, 0, st, parent_start, nparents, piece_first.get(), bins,
                hist.get(), child_start);

@@ -81,6 +81,8 @@ struct TextSource {
   __device__ __forceinline__ IdxT val(uint64_t i) const { return static_cast<IdxT>(base + i); }
   // the text window is re-read from L1/L2; compulsory traffic is the packed text itself (< 1 B)
   static constexpr uint64_t bytes_read_per_item() { return 1; }
+  // suffix i + 1 follows suffix i in the text: the MSD sort's level A loads the packed words once per thread
+  static constexpr bool kSequentialText = true;
 };
 
 // CAPSB_TRACE=1: per-stage / per-round log on stderr (host clock, pool occupancy)
@@ -202,11 +204,11 @@ void msd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key
     // level A: digit = top a bits of the key, records = (remaining bits << 32) | suffix
     msd_partition_level<MsdFirstSource<FirstSrc>, false>(
         dev, st, eng.msd_timers, eng.msd_timers.scatter_a, MsdFirstSource<FirstSrc>{first, 64u - key_bits, rem_a},
-        count, root.get(), 1, a, 2, FirstSrc::bytes_read_per_item(), start_a.get(), rec_a.get());
+        count, root.get(), 1, a, 2, 4, FirstSrc::bytes_read_per_item(), start_a.get(), rec_a.get());
     // level B: every level-A bucket by the next b bits
     msd_partition_level<MsdRecordSource, true>(dev, st, eng.msd_timers, eng.msd_timers.scatter_b,
                                                MsdRecordSource{rec_a.get(), 32u + rem_a - b, (1u << b) - 1u}, count,
-                                               start_a.get(), 1u << a, b, 8, sizeof(uint64_t), start_b.get(),
+                                               start_a.get(), 1u << a, b, 8, 1, sizeof(uint64_t), start_b.get(),
                                                keys_out);
   }
   // local sort of every bucket; the oversized ones are listed
@@ -1015,27 +1017,42 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
 //                of suffixes that have been tied (the rest is implicit, LocalRanks / ShardedRanks);
 //   last pass    LCPs at the edges of the key groups, bound by the shorter suffix inside them.
 // ---------------------------------------------------------------------------------------
-template <class IdxT, class Ranks>
-void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
-                        IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n, TiedSet<IdxT>& tied) {
-  using Comp = typename IdxTraits<IdxT>::Comp;
-  constexpr unsigned kField = IdxTraits<IdxT>::kField;
-  using Wide = unsigned __int128;
-  cudaStream_t st = eng.stream;
+// The refinement runs in three pieces so that the single-GPU path can finish the suffix array a
+// range of positions at a time (sa_build.cu streams every finished range to the host while the
+// next one is refined):
+//   refine_shallow  first pass, pair chains and text rounds on positions [0, count) of d_sa: local
+//                   to the range, no rank array.  Leaves the suffixes it could not separate (deep
+//                   ties: tandem arrays, long duplications, periodic texts) in `act`, at depth h.
+//   refine_deep     pair chains and rank rounds (prefix doubling) on whatever is left; needs the
+//                   ranks of the whole text, i.e. every range at the end of its shallow phase.
+//   fix_group_edges key-derived LCPs at the edges of the key groups and the shorter-suffix bound
+//                   inside them, for the listed tied positions (idempotent once the order is final).
+// refine_tied_groups runs the three in sequence over one range (the sharded path: a rank's bucket).
+template <class IdxT>
+struct RefineState {
+  ActiveList<IdxT> act;
+  uint64_t h = 0;             // symbols every group of act agrees on
+  uint64_t total_active = 0;  // over the ranks of the construction
+};
 
+template <class IdxT, class Ranks>
+void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys, IdxT* d_sa,
+                    IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n, TiedSet<IdxT>& tied,
+                    RefineState<IdxT>& state) {
+  cudaStream_t st = eng.stream;
   const unsigned log2_bits = pt.log2_bits;
 
   // The suffixes still to be ordered: members of key groups with at least two suffixes.  The same
   // pass writes every LCP that the keys alone decide (neighbours with different keys) and marks
   // the rest unset; entries next to a tied group are provisional (their bound depends on which
-  // member ends up at the group's edge) and are rewritten by the last pass of this function.
+  // member ends up at the group's edge) and are rewritten by fix_group_edges.
   // (all loads unconditional, on clamped indices: a short-circuit would chain their latencies)
   auto in_group = [=] __device__(uint64_t k) -> IdxT {
     const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
     const uint64_t a = keys[kp], b = keys[k], c = keys[kn];
     return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
   };
-  ActiveList<IdxT> act;
+  ActiveList<IdxT>& act = state.act;
   DevBuf<uint32_t> tied_bits;
   const bool vector_ok =
       ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(d_sa) | reinterpret_cast<uintptr_t>(d_lcp)) & 15u) == 0;
@@ -1050,7 +1067,7 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     IdxT total;
     read_back(st, &total, sc.total.get(), sizeof(IdxT));
     act.m = total;
-  } else {  // caller arrays that are not 16-byte aligned: the same pass, element by element
+  } else {  // arrays that are not 16-byte aligned: the same pass, element by element
     auto in_group_and_lcp = [=] __device__(uint64_t k) -> IdxT {
       const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
       const uint64_t a = keys[kp], b = keys[k], c = keys[kn];
@@ -1112,16 +1129,12 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
                  (unsigned long long)before, (unsigned long long)total_active, ms);
   };
 
-  // Two kinds of round.  TEXT rounds order every group by the text that follows the current
-  // depth (the next 63 bits of the packed text, read directly): they need no rank array, so in
-  // the sharded path they involve no exchange at all, and they clear the shallow ties — repeat
-  // families, accidental key collisions — which are nearly all of them.  RANK rounds are prefix
-  // doubling proper (second key = rank of suffix i + h): the depth doubles, which is what deep
-  // ties (tandem arrays, periodic texts) need.  The switch happens when a text round stops
-  // thinning the list; at that point every suffix that was ever tied publishes its group head
-  // once (never-tied suffixes keep implicit ranks, see LocalRanks / ShardedRanks).
+  // TEXT rounds order every group by the text that follows the current depth (the next 63 bits of
+  // the packed text, read directly): they need no rank array, so in the sharded path they involve
+  // no exchange at all, and they clear the shallow ties — repeat families, accidental key
+  // collisions — which are nearly all of them.  They stop when a round no longer thins the list:
+  // what is left needs the depth to double (refine_deep).
   const uint64_t text_step = 63u >> log2_bits;  // symbols a text round advances
-  bool rank_phase = false;
   bool try_pairs = true;
   for (unsigned iter = 0; total_active > 0; ++iter) {
     // groups of two are finished directly (order and LCP).  The step is a few passes over the
@@ -1129,7 +1142,7 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     if (try_pairs) {
       if (trace) round_start = std::chrono::steady_clock::now();
       const uint64_t before = total_active;
-      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h, rank_phase);
+      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h, false);
       total_active = ranks.global_sum(act.m);
       try_pairs = iter < 2 || (before - total_active) * 16 >= before;
       lap("pair chains", before);
@@ -1140,85 +1153,149 @@ void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigne
     const uint64_t m = act.m;
     const uint64_t before = total_active;
     const IdxT* idx = act.idx.get();
-    if (!rank_phase) {
-      // comp = 1 . (next 63 bits of text) for suffixes that reach depth h, else 0 . (n - 1 - i):
-      // the shorter suffix first, i.e. the larger position first
-      const PackedText text = pt;
-      const uint64_t depth = h;
-      DevBuf<uint64_t> comp(m, st);
-      uint64_t* c = comp.get();
-      launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
-        const uint64_t i = idx[t];
-        const uint64_t ih = i + depth;
-        c[t] = ih < n ? (1ull << 63) | (text.window(ih) >> 1) : (n - 1 - i);
-      });
-      refine_round<IdxT, uint64_t, false, Ranks>(eng, act, d_sa, pos_base, std::move(comp), 64, rank_bits, nullptr,
-                                                 TextRoundLcp<IdxT>{d_lcp, h, n, log2_bits});
-      h += text_step;
-      total_active = ranks.global_sum(act.m);
-      lap("text round", before);
-      // a text round that leaves more than 3/4 of the list tied: the rest is deep, switch to doubling
-      if (total_active > 0 && total_active * 4 > before * 3) {
-        if (trace) round_start = std::chrono::steady_clock::now();
-        rank_phase = true;
-        ranks.reset();
-        {  // every ever-tied suffix publishes its SA position; the still-tied ones then their group head
-          const IdxT* p0 = tied.pos.get();
-          DevBuf<IdxT> all_idx(tied.m, st), all_pos(tied.m, st);
-          IdxT* ai = all_idx.get();
-          IdxT* ap = all_pos.get();
-          launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
-            ai[t] = d_sa[p0[t]];
-            ap[t] = static_cast<IdxT>(pos_base + p0[t]);
-          });
-          ranks.publish(ai, ap, tied.m);
-        }
-        ranks.publish(act.idx.get(), act.group.get(), act.m);
-        lap("ranks published (switch to doubling)", total_active);
-      }
-    } else {
-      DevBuf<IdxT> second(m, st);
-      ranks.second_ranks(idx, m, h, second.get());
-      DevBuf<Comp> comp(m, st);
-      {
-        const IdxT* sec = second.get();
-        const IdxT* group = act.group.get();
-        Comp* c = comp.get();
-        launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
-          const bool inside = static_cast<uint64_t>(idx[t]) + h < n;
-          c[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
-                 static_cast<Comp>(sec[t]);
-        });
-      }
-      second.release();
-      refine_round<IdxT, Comp, true, Ranks>(eng, act, d_sa, pos_base, std::move(comp), rank_bits, rank_bits, &ranks);
-      if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
-      h <<= 1;
-      total_active = ranks.global_sum(act.m);
-      lap("rank round", before);
-    }
-  }
-
-  trace_point(eng, "ties resolved");
-  // key-derived LCPs at the two edges of every key group, now that the members there are final
-  {
-    const IdxT* p0 = tied.pos.get();
-    launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
-      const uint64_t k = p0[t];
-      if (k > 0) {
-        if (keys[k] != keys[k - 1]) {
-          d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
-        } else {  // inside a key group: a text round's entry is still to be bounded by the shorter suffix
-          const IdxT v = d_lcp[k];
-          const uint64_t a = d_sa[k - 1], b = d_sa[k];
-          const uint64_t shorter = n - (a > b ? a : b);
-          if (v != kLcpUnset<IdxT> && static_cast<uint64_t>(v) > shorter) d_lcp[k] = static_cast<IdxT>(shorter);
-        }
-      }
-      if (k + 1 < count && keys[k + 1] != keys[k])
-        d_lcp[k + 1] = key_lcp_value<IdxT>(keys[k], keys[k + 1], d_sa[k], d_sa[k + 1], n, log2_bits);
+    // comp = 1 . (next 63 bits of text) for suffixes that reach depth h, else 0 . (n - 1 - i):
+    // the shorter suffix first, i.e. the larger position first
+    const PackedText text = pt;
+    const uint64_t depth = h;
+    DevBuf<uint64_t> comp(m, st);
+    uint64_t* c = comp.get();
+    launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
+      const uint64_t i = idx[t];
+      const uint64_t ih = i + depth;
+      c[t] = ih < n ? (1ull << 63) | (text.window(ih) >> 1) : (n - 1 - i);
     });
+    refine_round<IdxT, uint64_t, false, Ranks>(eng, act, d_sa, pos_base, std::move(comp), 64, rank_bits, nullptr,
+                                               TextRoundLcp<IdxT>{d_lcp, h, n, log2_bits});
+    h += text_step;
+    total_active = ranks.global_sum(act.m);
+    lap("text round", before);
+    // a text round that leaves more than 3/4 of the list tied: the rest is deep
+    if (total_active > 0 && total_active * 4 > before * 3) break;
   }
+  state.h = h;
+  state.total_active = total_active;
+}
+
+// Prefix doubling proper on the suffixes refine_shallow left tied: second key = rank of suffix
+// i + h; h doubles, so deep ties cost O(log maxLCP) rounds.  `tied` lists every position of d_sa
+// that was ever tied (all ranges): those publish their SA position as rank once, the still-tied
+// ones then their group head; never-tied suffixes keep implicit ranks (LocalRanks / ShardedRanks).
+// state.act positions index d_sa, state.h is a depth every group agrees on.
+template <class IdxT, class Ranks>
+void refine_deep(Engine& eng, Ranks& ranks, IdxT* d_sa, IdxT* d_lcp, uint64_t pos_base, uint64_t n,
+                 const TiedSet<IdxT>& tied, RefineState<IdxT>& state) {
+  using Comp = typename IdxTraits<IdxT>::Comp;
+  constexpr unsigned kField = IdxTraits<IdxT>::kField;
+  cudaStream_t st = eng.stream;
+  ActiveList<IdxT>& act = state.act;
+  uint64_t h = state.h;
+  uint64_t total_active = state.total_active;
+  if (total_active == 0) return;
+  const unsigned rank_bits = round_up8(bit_length(n - 1));
+  const bool trace = trace_enabled();
+  std::chrono::steady_clock::time_point round_start;
+  auto lap = [&](const char* what, uint64_t before) {
+    if (!trace) return;
+    CAPSB_CUDA(cudaStreamSynchronize(st));
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - round_start).count();
+    std::fprintf(stderr, "[capsb] %s: h=%llu active %llu -> %llu  %.3f ms\n", what, (unsigned long long)h,
+                 (unsigned long long)before, (unsigned long long)total_active, ms);
+  };
+  if (trace) round_start = std::chrono::steady_clock::now();
+  ranks.reset();
+  {  // every ever-tied suffix publishes its SA position; the still-tied ones then their group head
+    const IdxT* p0 = tied.pos.get();
+    DevBuf<IdxT> all_idx(tied.m, st), all_pos(tied.m, st);
+    IdxT* ai = all_idx.get();
+    IdxT* ap = all_pos.get();
+    launch_map(eng.dev, st, tied.m, [=] __device__(uint64_t t) {
+      ai[t] = d_sa[p0[t]];
+      ap[t] = static_cast<IdxT>(pos_base + p0[t]);
+    });
+    ranks.publish(ai, ap, tied.m);
+  }
+  ranks.publish(act.idx.get(), act.group.get(), act.m);
+  lap("ranks published (switch to doubling)", total_active);
+
+  bool try_pairs = true;
+  for (unsigned iter = 0; total_active > 0; ++iter) {
+    if (try_pairs) {
+      if (trace) round_start = std::chrono::steady_clock::now();
+      const uint64_t before = total_active;
+      resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h, true);
+      total_active = ranks.global_sum(act.m);
+      try_pairs = iter < 2 || (before - total_active) * 16 >= before;
+      lap("pair chains", before);
+      if (total_active == 0) break;
+    }
+    eng.stats.refine_rounds++;
+    if (trace) round_start = std::chrono::steady_clock::now();
+    const uint64_t m = act.m;
+    const uint64_t before = total_active;
+    const IdxT* idx = act.idx.get();
+    DevBuf<IdxT> second(m, st);
+    ranks.second_ranks(idx, m, h, second.get());
+    DevBuf<Comp> comp(m, st);
+    {
+      const IdxT* sec = second.get();
+      const IdxT* group = act.group.get();
+      Comp* c = comp.get();
+      launch_map(eng.dev, st, m, [=] __device__(uint64_t t) {
+        const bool inside = static_cast<uint64_t>(idx[t]) + h < n;
+        c[t] = (static_cast<Comp>(static_cast<uint64_t>(group[t]) + (inside ? 1u : 0u)) << kField) |
+               static_cast<Comp>(sec[t]);
+      });
+    }
+    second.release();
+    refine_round<IdxT, Comp, true, Ranks>(eng, act, d_sa, pos_base, std::move(comp), rank_bits, rank_bits, &ranks);
+    if (h > (~0ull >> 2)) fail("internal: refinement did not converge");
+    h <<= 1;
+    total_active = ranks.global_sum(act.m);
+    lap("rank round", before);
+  }
+  state.h = h;
+  state.total_active = 0;
+}
+
+// Key-derived LCPs at the two edges of every key group and the shorter-suffix bound on the entries
+// the text rounds wrote inside them, for the tied positions pos[0, m) of d_sa[0, count) (valid
+// once the members at those positions are final; running it again later is harmless).
+template <class IdxT>
+void fix_group_edges(Engine& eng, const IdxT* pos, uint64_t m, const uint64_t* keys, const IdxT* d_sa, IdxT* d_lcp,
+                     uint64_t count, uint64_t n, unsigned log2_bits) {
+  launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) {
+    const uint64_t k = pos[t];
+    if (k > 0) {
+      if (keys[k] != keys[k - 1]) {
+        d_lcp[k] = key_lcp_value<IdxT>(keys[k - 1], keys[k], d_sa[k - 1], d_sa[k], n, log2_bits);
+      } else {  // inside a key group: a text round's entry is still to be bounded by the shorter suffix
+        const IdxT v = d_lcp[k];
+        const uint64_t a = d_sa[k - 1], b = d_sa[k];
+        const uint64_t shorter = n - (a > b ? a : b);
+        if (v != kLcpUnset<IdxT> && static_cast<uint64_t>(v) > shorter) d_lcp[k] = static_cast<IdxT>(shorter);
+      }
+    }
+    if (k + 1 < count && keys[k + 1] != keys[k])
+      d_lcp[k + 1] = key_lcp_value<IdxT>(keys[k], keys[k + 1], d_sa[k], d_sa[k + 1], n, log2_bits);
+  });
+}
+
+// ---------------------------------------------------------------------------------------
+// Refinement of the ties the key sort leaves.  d_sa[0..count) holds suffixes in key order (SA
+// positions pos_base .. pos_base + count of the final array); keys[] are their (masked) keys,
+// which order them by their first h0 symbols.  Groups of equal keys must be complete inside
+// [0, count).  On return d_sa is in suffix order, d_lcp holds every entry except those of
+// neighbours that stayed tied into the rank rounds (kLcpUnset: the permuted-LCP stage of the
+// caller, collect_deep_pairs + plcp_for_pairs), and `tied` lists the positions that were tied.
+// ---------------------------------------------------------------------------------------
+template <class IdxT, class Ranks>
+void refine_tied_groups(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned key_bits, const uint64_t* keys,
+                        IdxT* d_sa, IdxT* d_lcp, uint64_t count, uint64_t pos_base, uint64_t n, TiedSet<IdxT>& tied) {
+  RefineState<IdxT> state;
+  refine_shallow<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, count, pos_base, n, tied, state);
+  refine_deep<IdxT>(eng, ranks, d_sa, d_lcp, pos_base, n, tied, state);
+  trace_point(eng, "ties resolved");
+  fix_group_edges<IdxT>(eng, tied.pos.get(), tied.m, keys, d_sa, d_lcp, count, n, pt.log2_bits);
 }
 
 // LCP of local position 0: against (prev_key, prev_idx), the last suffix of the bucket before
