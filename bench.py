@@ -369,6 +369,8 @@ def main():
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     e2e_ms = max(ev2.elapsed_time(ev3) / args.steps, e2e_wall_ms)
     clocks = sampler.stop()
+    e2e_stats = eng.stats()  # of the last end-to-end step
+    e2e_parts = {k: round(e2e_stats[k], 3) for k in ("ms_h2d", "ms_pack", "ms_sort", "ms_refine", "ms_deep_lcp", "ms_total", "ms_d2h")}
 
     # the device-resident leg left the same arrays in HBM as the end-to-end leg left in the host buffers
     # (all n entries of SA and LCP, compared on the device piece by piece)
@@ -412,7 +414,10 @@ def main():
                                 f"{last_stats['msd_large_buckets']} oversized buckets ({last_stats['msd_large_records']} records) by the LSD passes"
                                 if last_stats["msd_a_bits"] else "LSD passes")},
         "e2e": {"value": n / (e2e_ms / 1e3), "unit": "suffixes/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": n, "d2h_bytes_per_step": 2 * 4 * n, "matches_device_result": same},
+                "h2d_bytes_per_step": n, "d2h_bytes_per_step": 2 * 4 * n, "matches_device_result": same,
+                "last_step_ms": e2e_parts,
+                "note": "ms_total = compute stream, ms_d2h = first result copy issued .. last byte on the host; the ranges of "
+                        "SA/LCP positions are copied out while later ranges are still being refined"},
         "verified": verified,
         "gpu_launches": int(launches),
         "stage_ms": {k: round(v, 3) for k, v in stage_ms.items()},

@@ -86,30 +86,48 @@ template <class IdxT>
 struct ResultCopy {
   Engine& eng;
   EventPair d2h;
-  ResultCopy(Engine& e, IdxT* sa_out) : eng(e) {
+  ResultCopy(Engine& e, IdxT* sa_out, IdxT* lcp_out = nullptr) : eng(e) {
     // CAPSB_EARLY_SA=0: measurement switch, both copies after the construction
     const char* env = std::getenv("CAPSB_EARLY_SA");
-    eng.sa_sink = (env && env[0] == '0') ? nullptr : sa_out;
+    const bool early = !(env && env[0] == '0');
+    eng.sa_sink = early ? sa_out : nullptr;
+    eng.lcp_sink = early ? lcp_out : nullptr;
+    eng.sa_sink_dev = eng.lcp_sink_dev = nullptr;
+    if (early && sa_out && lcp_out) {
+      // streaming needs the caller's arrays in the device's address space (pinned host memory)
+      void *sa_dev = nullptr, *lcp_dev = nullptr;
+      if (cudaHostGetDevicePointer(&sa_dev, sa_out, 0) == cudaSuccess &&
+          cudaHostGetDevicePointer(&lcp_dev, lcp_out, 0) == cudaSuccess) {
+        eng.sa_sink_dev = sa_dev;
+        eng.lcp_sink_dev = lcp_dev;
+      } else {
+        cudaGetLastError();
+      }
+    }
     eng.sa_sink_started = d2h.a;
     eng.sa_sunk = false;
+    eng.results_streamed = false;
   }
   ~ResultCopy() {
-    eng.sa_sink = nullptr;
+    eng.sa_sink = eng.lcp_sink = nullptr;
+    eng.sa_sink_dev = eng.lcp_sink_dev = nullptr;
     eng.sa_sink_started = nullptr;
     cudaStreamSynchronize(eng.copy_stream);  // no copy into the caller's arrays outlives the call
   }
   // d_sa / d_lcp [0, count) = entries [first, first + count) of the full arrays
-  void finish(const IdxT* d_sa, const IdxT* d_lcp, IdxT* sa_out, IdxT* lcp_out, uint64_t first, uint64_t count) {
+  void finish(const IdxT* d_sa, const IdxT* d_lcp, IdxT* sa_out, IdxT* lcp_out, uint64_t first, uint64_t count,
+              bool lcp_changed_after_build = false) {
     cudaStream_t cs = eng.copy_stream;
     eng.sa_sink = nullptr;
     CAPSB_CUDA(cudaEventRecord(d2h.b, eng.stream));
     CAPSB_CUDA(cudaStreamWaitEvent(cs, d2h.b, 0));
+    const bool streamed = eng.results_streamed && !lcp_changed_after_build;
     if (!eng.sa_sunk) {
       CAPSB_CUDA(cudaEventRecord(d2h.a, cs));
       if (count)
         CAPSB_CUDA(cudaMemcpyAsync(sa_out + first, d_sa, count * sizeof(IdxT), cudaMemcpyDeviceToHost, cs));
     }
-    if (count)
+    if (count && !streamed)
       CAPSB_CUDA(cudaMemcpyAsync(lcp_out + first, d_lcp, count * sizeof(IdxT), cudaMemcpyDeviceToHost, cs));
     CAPSB_CUDA(cudaEventRecord(d2h.b, cs));
     CAPSB_CUDA(cudaStreamSynchronize(cs));
@@ -133,7 +151,9 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
     capsb::DevBuf<uint8_t> d_text(n, st);
     capsb::DevBuf<IdxT> d_sa(n, st), d_lcp(n, st);
     EventPair h2d;
-    ResultCopy<IdxT> results(eng, sa_out);
+    // (a bounded context clamps the LCP array after the construction: no streaming then)
+    const bool clamps = max_context != 0 && max_context < n;
+    ResultCopy<IdxT> results(eng, sa_out, clamps ? nullptr : lcp_out);
     CAPSB_CUDA(cudaEventRecord(h2d.a, st));
     CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
     CAPSB_CUDA(cudaEventRecord(h2d.b, st));

@@ -84,6 +84,19 @@ struct Engine {
   bool sa_sunk = false;
   // d_sa[0, count) = SA[first, first + count) is final
   void sa_is_final(const void* d_sa, uint64_t first, uint64_t count, size_t idx_bytes);
+  // Single-GPU host-buffer construction: the path finishes SA and LCP a range of positions at a
+  // time and copies every finished range to the caller's arrays while the next one is computed
+  // (PCIe is the longest leg of the call).  The few entries that only the last stage settles — the
+  // deep ties — are written afterwards, straight into the host arrays by a kernel, which needs
+  // them mapped into the device's address space (pinned memory); lcp_sink_dev == nullptr turns the
+  // streaming off and everything is copied once at the end.
+  void* lcp_sink = nullptr;
+  void* sa_sink_dev = nullptr;
+  void* lcp_sink_dev = nullptr;
+  bool results_streamed = false;  // every entry of SA and LCP has been sent to the host arrays
+  bool can_stream() const { return sa_sink && lcp_sink && sa_sink_dev && lcp_sink_dev; }
+  // entries [first, first + count) of both device arrays (indexed like the full arrays) are final
+  void range_is_final(const void* d_sa, const void* d_lcp, uint64_t first, uint64_t count, size_t idx_bytes);
   // sharded construction (multi-process): the transport this engine joined and its last shard
   std::unique_ptr<Comm> comm;
   ShardResult<uint32_t> shard32;

@@ -523,7 +523,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
 
 static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_local_kernel(uint64_t* __restrict__ recs,
                                                                   const uint32_t* __restrict__ child_start,
-                                                                  uint32_t nbuckets, unsigned key_bits,
+                                                                  uint32_t q_begin, uint32_t q_end, unsigned key_bits,
                                                                   unsigned prefix_bits, uint32_t* __restrict__ sa_out,
                                                                   uint32_t* __restrict__ large_list,
                                                                   uint32_t* __restrict__ large_count) {
@@ -535,7 +535,7 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
   for (unsigned b = tid; b < static_cast<unsigned>(kMsdLocalPadded); b += kMsdThreads) sm.cnt[b] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
-  for (uint32_t q = blockIdx.x; q < nbuckets; q += gridDim.x) {
+  for (uint32_t q = q_begin + blockIdx.x; q < q_end; q += gridDim.x) {
     const uint32_t beg = child_start[q];
     const uint32_t count = child_start[q + 1] - beg;
     if (count == 0) continue;
@@ -546,8 +546,7 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
     // The first counting pass takes the top hb of the remaining bits: about one counter per two
     // records (the scan of the counters is per-bucket overhead), at least rem_bits - 12 so that
     // one more pass can finish a large group, at most 12.
-    unsigned hb = 1;
-    while ((2u << hb) < count) ++hb;
+    unsigned hb = count > 4 ? 31u - static_cast<unsigned>(__clz(count - 1u)) : 1u;  // smallest hb with 2^(hb+1) >= count
     if (hb > static_cast<unsigned>(kMsdLocalBits)) hb = kMsdLocalBits;
     if (hb + kMsdLocalBits < rem_bits) hb = rem_bits - kMsdLocalBits;
     if (hb > rem_bits) hb = rem_bits;

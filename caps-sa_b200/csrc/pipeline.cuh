@@ -180,20 +180,33 @@ inline bool msd_sort_enabled() {
 }
 
 // The packed-record MSD sort (msd_sort.cuh) of `count` suffixes given by `first` (key(i) = masked
-// text window of the i-th suffix, val(i) = the suffix).  keys_out doubles as the level-B record
-// buffer: the local sort turns it into the sorted keys in place.
+// text window of the i-th suffix, val(i) = the suffix), in two parts: msd_partition runs levels A
+// and B over everything (keys_out doubles as the level-B record buffer); msd_local_sort finishes
+// the buckets [q_begin, q_end) — sorted keys in place of the records, suffixes to sa_out — so a
+// caller can finish the suffix array a range of positions at a time.
+struct MsdSorted {
+  unsigned a = 0, b = 0, key_bits = 0;
+  uint64_t count = 0;
+  uint32_t nbuckets = 0;
+  DevBuf<uint32_t> start_b;        // nbuckets + 1 bucket starts
+  std::vector<uint32_t> a_starts;  // host copy of the 2^a + 1 level-A bucket starts (on request)
+  DevBuf<uint32_t> large_list, large_count;
+};
+
 template <class FirstSrc>
-void msd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
-                       uint32_t* sa_out) {
+void msd_partition(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out, MsdSorted& ms,
+                   bool want_a_starts) {
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
   const MsdPlan plan = msd_plan(count, key_bits);
   const unsigned a = plan.a, b = plan.b;
   const unsigned rem_a = key_bits - a;  // <= 32: the record's key field after level A
+  ms.a = a, ms.b = b, ms.key_bits = key_bits, ms.count = count;
+  ms.nbuckets = 1u << (a + b);
   eng.stats.msd_a_bits = a;
   eng.stats.msd_b_bits = b;
-  const uint32_t nbuckets = 1u << (a + b);
-  DevBuf<uint32_t> root(2, st), start_a((1u << a) + 1, st), start_b(static_cast<uint64_t>(nbuckets) + 1, st);
+  DevBuf<uint32_t> root(2, st), start_a((1u << a) + 1, st);
+  ms.start_b.alloc(static_cast<uint64_t>(ms.nbuckets) + 1, st);
   {
     uint32_t* r = root.get();
     const uint32_t c = static_cast<uint32_t>(count);
@@ -208,26 +221,48 @@ void msd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key
     // level B: every level-A bucket by the next b bits
     msd_partition_level<MsdRecordSource, true>(dev, st, eng.msd_timers, eng.msd_timers.scatter_b,
                                                MsdRecordSource{rec_a.get(), 32u + rem_a - b, (1u << b) - 1u}, count,
-                                               start_a.get(), 1u << a, b, 8, 1, sizeof(uint64_t), start_b.get(),
+                                               start_a.get(), 1u << a, b, 8, 1, sizeof(uint64_t), ms.start_b.get(),
                                                keys_out);
   }
-  // local sort of every bucket; the oversized ones are listed
-  DevBuf<uint32_t> large_list(count / kMsdLocalCap + 1, st), large_count(1, st);
-  CAPSB_CUDA(cudaMemsetAsync(large_count.get(), 0, sizeof(uint32_t), st));
+  if (want_a_starts) {
+    ms.a_starts.resize((1u << a) + 1);
+    read_back(st, ms.a_starts.data(), start_a.get(), ms.a_starts.size() * sizeof(uint32_t));
+  }
+  ms.large_list.alloc(count / kMsdLocalCap + 1, st);
+  ms.large_count.alloc(1, st);
+}
+
+inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint32_t* sa_out, uint32_t q_begin,
+                           uint32_t q_end, uint64_t records) {
+  cudaStream_t st = eng.stream;
+  const DeviceInfo& dev = eng.dev;
+  if (q_begin >= q_end) return;
+  CAPSB_CUDA(cudaMemsetAsync(ms.large_count.get(), 0, sizeof(uint32_t), st));
   {
     constexpr size_t kSmem = sizeof(MsdLocalSmem);
     msd_allow_smem(msd_local_kernel, kSmem);
-    const uint32_t grid = std::min<uint32_t>(nbuckets, static_cast<uint32_t>(dev.sm_count) * 2u);
-    MsdTimed timed(eng.msd_timers.local, st, count * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
-    CAPSB_LAUNCH(msd_local_kernel, grid, kMsdThreads, kSmem, st, keys_out, start_b.get(), nbuckets, key_bits, a + b,
-                 sa_out, large_list.get(), large_count.get());
+    const uint32_t grid = std::min<uint32_t>(q_end - q_begin, static_cast<uint32_t>(dev.sm_count) * 2u);
+    MsdTimed timed(eng.msd_timers.local, st, records * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
+    CAPSB_LAUNCH(msd_local_kernel, grid, kMsdThreads, kSmem, st, keys_out, ms.start_b.get(), q_begin, q_end,
+                 ms.key_bits, ms.a + ms.b, sa_out, ms.large_list.get(), ms.large_count.get());
   }
   uint32_t nlarge = 0;
-  read_back(st, &nlarge, large_count.get(), sizeof(uint32_t));
-  eng.stats.msd_large_buckets = nlarge;
-  if (nlarge > 0)
-    msd_sort_large_buckets(dev, st, eng.radix, keys_out, sa_out, start_b.get(), large_list.get(), nlarge, key_bits,
-                           a + b, eng.scan32, &eng.stats.msd_large_records);
+  read_back(st, &nlarge, ms.large_count.get(), sizeof(uint32_t));
+  eng.stats.msd_large_buckets += nlarge;
+  if (nlarge > 0) {
+    uint64_t large_records = 0;
+    msd_sort_large_buckets(dev, st, eng.radix, keys_out, sa_out, ms.start_b.get(), ms.large_list.get(), nlarge,
+                           ms.key_bits, ms.a + ms.b, eng.scan32, &large_records);
+    eng.stats.msd_large_records += large_records;
+  }
+}
+
+template <class FirstSrc>
+void msd_sort_suffixes(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bits, uint64_t* keys_out,
+                       uint32_t* sa_out) {
+  MsdSorted ms;
+  msd_partition(eng, first, count, key_bits, keys_out, ms, false);
+  msd_local_sort(eng, ms, keys_out, sa_out, 0, ms.nbuckets, count);
 }
 
 // The LSD sort: stable 8-bit passes over (u64 key, suffix) pairs, the first one reading the keys
@@ -420,8 +455,8 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
                                                                        const IdxT* __restrict__ sa,
                                                                        IdxT* __restrict__ lcp,
                                                                        uint32_t* __restrict__ tied_bits, uint64_t count,
-                                                                       uint64_t chunk, uint64_t n, unsigned log2_bits,
-                                                                       IdxT* __restrict__ partial) {
+                                                                       uint64_t skip, uint64_t chunk, uint64_t n,
+                                                                       unsigned log2_bits, IdxT* __restrict__ partial) {
   __shared__ unsigned warp_sums[kKeyLcpThreads / 32];
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;  // a multiple of 128
   const uint64_t end = begin + chunk < count ? begin + chunk : count;
@@ -433,6 +468,9 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
     IdxT s[4], l[4];
     uint64_t prev_key, next_key;
     IdxT prev_sa;
+    // (the first `skip` positions pad the arrays to 16-byte alignment: they belong to the range
+    // of positions before this one and are neither counted nor written)
+    const bool whole_row = wbase + 128 <= end && wbase >= skip;
     if (wbase + 128 <= end) {  // warp-uniform: the whole row of 128 positions exists
       load4(keys + k0, key);
       load4(sa + k0, s);
@@ -462,19 +500,19 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
       const uint64_t pk = j ? key[j - 1] : prev_key;
       const uint64_t ps = j ? s[j - 1] : prev_sa;
       const uint64_t nk = j < 3 ? key[j + 1] : next_key;
-      const bool exists = k0 + j < end;
+      const bool exists = (k0 + j < end) & (k0 + j >= skip);
       const bool eq_prev = pk == key[j];
       // past the end of the array the clamped loads repeat the last element: not a neighbour
       const bool eq_next = (nk == key[j]) & (k0 + j + 1 < count);
       l[j] = eq_prev ? kLcpUnset<IdxT> : key_lcp_value<IdxT>(pk, key[j], ps, s[j], n, log2_bits);
       nib |= (exists & (eq_prev | eq_next)) ? 1u << j : 0u;
     }
-    if (wbase + 128 <= end) {
+    if (whole_row) {
       store4(lcp + k0, l);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (k0 + j < end) lcp[k0 + j] = l[j];
+        if (k0 + j < end && k0 + j >= skip) lcp[k0 + j] = l[j];
     }
     tied_here += __popc(nib);
     // 8 lanes x 4 flags = one 32-bit word of the bitmap
@@ -1054,15 +1092,21 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
   };
   ActiveList<IdxT>& act = state.act;
   DevBuf<uint32_t> tied_bits;
+  // The streaming pass wants 16-byte aligned arrays.  A range that starts in the middle of larger
+  // arrays (sa_build.cu: one range of positions at a time) is reached by stepping back `skip` < 4
+  // positions — entries of the range before it, which the pass reads but neither counts nor writes.
+  const uint64_t skip = (reinterpret_cast<uintptr_t>(d_sa) & 15u) / sizeof(IdxT);
   const bool vector_ok =
-      ((reinterpret_cast<uintptr_t>(keys) | reinterpret_cast<uintptr_t>(d_sa) | reinterpret_cast<uintptr_t>(d_lcp)) & 15u) == 0;
+      skip <= pos_base &&
+      ((reinterpret_cast<uintptr_t>(keys - skip) | reinterpret_cast<uintptr_t>(d_sa - skip) |
+        reinterpret_cast<uintptr_t>(d_lcp - skip)) & 15u) == 0;
   if (vector_ok) {
     // one streaming sweep: key-derived LCPs, tied bitmap, tied count per chunk (key_lcp_count_kernel)
     ScanScratch<IdxT>& sc = eng.scan_scratch<IdxT>();
-    const Chunking ck = make_chunking(count, kScanTile, sc.max_blocks);
-    tied_bits.alloc(count / 32 + 8, st);
-    CAPSB_LAUNCH((key_lcp_count_kernel<IdxT>), ck.blocks, kKeyLcpThreads, 0, st, keys, d_sa, d_lcp, tied_bits.get(),
-                 count, ck.chunk, n, log2_bits, sc.partial.get());
+    const Chunking ck = make_chunking(count + skip, kScanTile, sc.max_blocks);
+    tied_bits.alloc((count + skip) / 32 + 8, st);
+    CAPSB_LAUNCH((key_lcp_count_kernel<IdxT>), ck.blocks, kKeyLcpThreads, 0, st, keys - skip, d_sa - skip, d_lcp - skip,
+                 tied_bits.get(), count + skip, skip, ck.chunk, n, log2_bits, sc.partial.get());
     CAPSB_LAUNCH((scan_spine_kernel<IdxT, OpSum>), 1, kScanThreads, 0, st, ck.blocks, sc.partial.get(), sc.total.get());
     IdxT total;
     read_back(st, &total, sc.total.get(), sizeof(IdxT));
@@ -1095,8 +1139,13 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
     };
     if (vector_ok) {
       const uint32_t* bits = tied_bits.get();
+      const IdxT* sa_al = d_sa - skip;
       select_finish<IdxT>(
-          eng, count, [=] __device__(uint64_t k) -> IdxT { return (bits[k >> 5] >> (k & 31u)) & 1u; }, collect);
+          eng, count + skip, [=] __device__(uint64_t k) -> IdxT { return (bits[k >> 5] >> (k & 31u)) & 1u; },
+          [=] __device__(uint64_t k, IdxT slot) {  // k counts from the aligned start
+            p[slot] = p0[slot] = static_cast<IdxT>(k - skip);
+            s[slot] = sa_al[k];
+          });
     } else {
       select_finish<IdxT>(eng, count, in_group, collect);
     }

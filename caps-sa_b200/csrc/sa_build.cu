@@ -12,6 +12,9 @@
 //       comparison on the irreducible ones (sum of irreducible LCPs <= 2 n log n).
 // The output is the canonical SA/LCP under signed-char order, shorter suffix first —
 // bit-identical to the reference at its default (unbounded) context.
+#include <cstdlib>
+#include <vector>
+
 #include "comm.cuh"
 #include "pipeline.cuh"
 
@@ -66,6 +69,64 @@ void Engine::sa_is_final(const void* d_sa, uint64_t first, uint64_t count, size_
   sa_sunk = true;
 }
 
+void Engine::range_is_final(const void* d_sa, const void* d_lcp, uint64_t first, uint64_t count, size_t idx_bytes) {
+  if (!can_stream() || count == 0) return;
+  cudaEvent_t ready;
+  if (!events.empty()) {
+    ready = events.back();
+    events.pop_back();
+  } else {
+    CAPSB_CUDA(cudaEventCreate(&ready));
+  }
+  CAPSB_CUDA(cudaEventRecord(ready, stream));
+  CAPSB_CUDA(cudaStreamWaitEvent(copy_stream, ready, 0));
+  events.push_back(ready);  // the wait has captured this recording
+  if (!sa_sunk && sa_sink_started) CAPSB_CUDA(cudaEventRecord(sa_sink_started, copy_stream));
+  CAPSB_CUDA(cudaMemcpyAsync(static_cast<char*>(sa_sink) + first * idx_bytes, static_cast<const char*>(d_sa) + first * idx_bytes,
+                             count * idx_bytes, cudaMemcpyDeviceToHost, copy_stream));
+  CAPSB_CUDA(cudaMemcpyAsync(static_cast<char*>(lcp_sink) + first * idx_bytes, static_cast<const char*>(d_lcp) + first * idx_bytes,
+                             count * idx_bytes, cudaMemcpyDeviceToHost, copy_stream));
+  sa_sunk = true;
+}
+
+namespace {
+
+// Ranges of SA positions that the single-GPU path finishes one after the other.  Boundaries are
+// starts of level-A buckets of the key sort, so no key group (hence no tie group) spans one.
+struct RangePlan {
+  std::vector<uint64_t> bound;    // bound[r] .. bound[r + 1]: SA positions of range r
+  std::vector<uint32_t> a_index;  // a_index[r] .. a_index[r + 1]: its level-A buckets
+};
+
+RangePlan plan_ranges(uint64_t n, const std::vector<uint32_t>& a_starts, uint64_t want) {
+  RangePlan plan;
+  const uint32_t buckets = static_cast<uint32_t>(a_starts.size()) - 1;
+  plan.bound.push_back(0);
+  plan.a_index.push_back(0);
+  if (want < 1) want = 1;
+  const uint64_t target = (n + want - 1) / want;
+  for (uint32_t x = 1; x < buckets; ++x) {
+    const uint64_t here = a_starts[x];
+    if (here - plan.bound.back() >= target && n - here > 0 && here > plan.bound.back()) {
+      plan.bound.push_back(here);
+      plan.a_index.push_back(x);
+    }
+  }
+  plan.bound.push_back(n);
+  plan.a_index.push_back(buckets);
+  return plan;
+}
+
+uint64_t ranges_wanted(const Engine& eng, uint64_t n) {
+  if (const char* env = std::getenv("CAPSB_STREAM_RANGES")) return static_cast<uint64_t>(std::atoll(env));
+  if (!eng.can_stream()) return 1;
+  // a range's copy (8 bytes per position over PCIe) should dwarf the fixed cost of refining it
+  const uint64_t want = n / (96ull << 20);
+  return want < 1 ? 1 : (want > 32 ? 32 : want);
+}
+
+}  // namespace
+
 template <class IdxT>
 void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, IdxT* d_lcp) {
   CAPSB_CUDA(cudaSetDevice(eng.dev.device));
@@ -76,6 +137,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   eng.msd_timers.reset();
   eng.stats.n = n;
   eng.stats.idx_bytes = sizeof(IdxT);
+  eng.results_streamed = false;
   if (n == 0) return;
   if (sizeof(IdxT) == 4 && n > 0xFFFFFFFFull) fail("text too long for 32-bit indices");
 
@@ -90,31 +152,129 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   eng.stats.alphabet_size = packed.sigma;
   clock.mark();  // 1
 
-  // ---- 2. key sort of all suffixes (leading key_bits of the packed prefix, stable LSD passes) ---
+  // ---- 2. key sort (leading key_bits of the packed prefix) ---------------------------------
+  // Packed-record MSD sort: the two partition levels run over everything, the buckets are then
+  // finished range by range, each range followed at once by its share of step 3 and by its copy to
+  // the host.  LSD passes (64-bit indices): one range.
   const unsigned key_bits = choose_key_bits(n);
   eng.stats.key_bits = key_bits;
   DevBuf<uint64_t> key_buf(n, st);
-  sort_suffix_slice<IdxT>(eng, pt, 0, n, key_bits, key_buf.get(), d_sa);
-  const uint64_t* keys = key_buf.get();
-  clock.mark();  // 2
-  clock.mark();  // 3
-
-  // ---- 3. ties: prefix-doubling refinement + pair chains; LCPs the keys decide ---------------
-  TiedSet<IdxT> tied;
-  {
-    LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
-    refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, n, 0, n, tied);
+  uint64_t* keys = key_buf.get();
+  const TextSource<IdxT> first{pt, key_mask_of(key_bits), 0};
+  bool msd = false;
+  MsdSorted ms;
+  RangePlan ranges;
+  ranges.bound = {0, n};
+  ranges.a_index = {0, 0};
+  if constexpr (sizeof(IdxT) == 4) {
+    msd = msd_sort_enabled() && msd_applicable(key_bits);
+    if (msd) {
+      const uint64_t want = ranges_wanted(eng, n);
+      msd_partition(eng, first, n, key_bits, keys, ms, true);
+      ranges = plan_ranges(n, ms.a_starts, want);
+    }
   }
-  eng.sa_is_final(d_sa, 0, n, sizeof(IdxT));
-  first_position_lcp<IdxT>(eng, keys, d_sa, d_lcp, n, n, log2_bits, false, 0, 0);
-  eng.stats.tied_after_key_sort = tied.m;
-  clock.mark();  // 4
+  if (!msd) lsd_sort_suffixes<IdxT>(eng, first, n, key_bits, keys, d_sa);
+  const size_t range_count = ranges.bound.size() - 1;
+  const bool streaming = range_count > 1 && eng.can_stream();
+  clock.mark();  // 2
+  float ms_local = 0, ms_shallow = 0;
+
+  // ---- 3. ties: per range, the shallow part of the refinement (pair chains + text rounds) ------
+  LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
+  std::vector<TiedSet<IdxT>> tied_of(range_count);
+  std::vector<RefineState<IdxT>> state_of(range_count);
+  for (size_t r = 0; r < range_count; ++r) {
+    const uint64_t lo = ranges.bound[r], count = ranges.bound[r + 1] - lo;
+    clock.mark("range: begin");
+    if constexpr (sizeof(IdxT) == 4) {
+      if (msd)
+        msd_local_sort(eng, ms, keys, d_sa, ranges.a_index[r] << ms.b, ranges.a_index[r + 1] << ms.b, count);
+    }
+    clock.mark("range: buckets sorted");
+    refine_shallow<IdxT>(eng, ranks, pt, key_bits, keys + lo, d_sa + lo, d_lcp + lo, count, lo, n, tied_of[r],
+                         state_of[r]);
+    fix_group_edges<IdxT>(eng, tied_of[r].pos.get(), tied_of[r].m, keys + lo, d_sa + lo, d_lcp + lo, count, n, log2_bits);
+    {  // the range's first position against the last suffix of the range before it (a different key)
+      IdxT* lcp_here = d_lcp + lo;
+      const IdxT* sa_here = d_sa + lo;
+      const uint64_t* keys_here = keys + lo;
+      const bool has_prev = lo > 0;
+      launch_map(eng.dev, st, 1, [=] __device__(uint64_t) {
+        lcp_here[0] = has_prev ? key_lcp_value<IdxT>(keys_here[-1], keys_here[0], sa_here[-1], sa_here[0], n, log2_bits)
+                               : IdxT(0);
+      });
+    }
+    if (streaming) eng.range_is_final(d_sa, d_lcp, lo, count, sizeof(IdxT));
+    clock.mark("range: shallow ties resolved");
+    eng.stats.tied_after_key_sort += tied_of[r].m;
+  }
+
+  // ---- 3b. what the text rounds could not separate: prefix doubling over all ranges at once ------
+  // (the lists are concatenated in range order = SA order; positions become positions of d_sa)
+  TiedSet<IdxT> tied;
+  RefineState<IdxT> deep;
+  deep.h = ~0ull;
+  for (size_t r = 0; r < range_count; ++r) {
+    tied.m += tied_of[r].m;
+    deep.act.m += state_of[r].act.m;
+    if (state_of[r].act.m && state_of[r].h < deep.h) deep.h = state_of[r].h;
+  }
+  deep.total_active = deep.act.m;
+  DevBuf<IdxT> deep_pos(deep.act.m, st);  // the positions the deep stages may still change
+  if (range_count == 1) {
+    tied = std::move(tied_of[0]);
+    deep.act = std::move(state_of[0].act);
+  } else {
+    tied.pos.alloc(tied.m, st);
+    deep.act.pos.alloc(deep.act.m, st);
+    deep.act.idx.alloc(deep.act.m, st);
+    deep.act.group.alloc(deep.act.m, st);
+    uint64_t tied_at = 0, act_at = 0;
+    for (size_t r = 0; r < range_count; ++r) {
+      const IdxT lo = static_cast<IdxT>(ranges.bound[r]);
+      {
+        const IdxT* src = tied_of[r].pos.get();
+        IdxT* dst = tied.pos.get() + tied_at;
+        launch_map(eng.dev, st, tied_of[r].m, [=] __device__(uint64_t t) { dst[t] = src[t] + lo; });
+        tied_at += tied_of[r].m;
+      }
+      {
+        const ActiveList<IdxT>& a = state_of[r].act;
+        const IdxT* sp = a.pos.get();
+        const IdxT* si = a.idx.get();
+        const IdxT* sg = a.group.get();
+        IdxT* dp = deep.act.pos.get() + act_at;
+        IdxT* di = deep.act.idx.get() + act_at;
+        IdxT* dg = deep.act.group.get() + act_at;
+        launch_map(eng.dev, st, a.m, [=] __device__(uint64_t t) {
+          dp[t] = sp[t] + lo;
+          di[t] = si[t];
+          dg[t] = sg[t];
+        });
+        act_at += a.m;
+      }
+      tied_of[r] = TiedSet<IdxT>();
+      state_of[r] = RefineState<IdxT>();
+    }
+  }
+  const uint64_t deep_count = deep.act.m;
+  if (deep_count) CAPSB_CUDA(cudaMemcpyAsync(deep_pos.get(), deep.act.pos.get(), deep_count * sizeof(IdxT), cudaMemcpyDeviceToDevice, st));
+  refine_deep<IdxT>(eng, ranks, d_sa, d_lcp, 0, n, tied, deep);
+  if (deep_count)
+    fix_group_edges<IdxT>(eng, deep_pos.get(), deep_count, keys, d_sa, d_lcp, n, n, log2_bits);
+  if (!streaming) eng.sa_is_final(d_sa, 0, n, sizeof(IdxT));
+  clock.mark();  // after the deep ties
 
   // ---- 4. LCP of the tied neighbours still open: permuted-LCP recurrence ---------------------
-  if (tied.m > 0) {
+  // (only neighbours that stayed tied into the rank rounds: positions listed in deep_pos)
+  if (deep_count > 0) {
+    TiedSet<IdxT> open;
+    open.m = deep_count;
+    open.pos = std::move(deep_pos);
     // the pairs (i = SA[k], j = SA[k-1]) keyed by i; j and k travel as the sort's value
     DevBuf<IdxT> pos_a, pair_j, pair_k;
-    const uint64_t m = collect_deep_pairs<IdxT>(eng, tied, keys, d_sa, d_lcp, pos_a, pair_j, pair_k);
+    const uint64_t m = collect_deep_pairs<IdxT>(eng, open, keys, d_sa, d_lcp, pos_a, pair_j, pair_k);
     DevBuf<IdxT> pos_b(m, st);
     DevBuf<IdxPair<IdxT>> tag_a(m, st), tag_b(m, st);
     {
@@ -133,17 +293,61 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     plcp_for_pairs<IdxT>(
         eng, pt, pos_i, [=] __device__(uint64_t t) -> uint64_t { return tag[t].a; }, m, 0,
         [=] __device__(uint64_t t, IdxT lcp, uint64_t, IdxT) { d_lcp[tag[t].b] = lcp; });
+    deep_pos = std::move(open.pos);
   }
-  clock.mark();  // 5
+  // ---- 5. streamed results: the entries the deep stages settled go to the host arrays directly ----
+  if (streaming) {
+    if (deep_count * 8 > n) {
+      // most of the text is deep ties (periodic texts): nothing was gained by the early copies,
+      // the caller copies both arrays again
+      eng.results_streamed = false;
+      eng.sa_sunk = false;
+    } else {
+      if (deep_count > 0) {
+        cudaEvent_t done;
+        if (!eng.events.empty()) {
+          done = eng.events.back();
+          eng.events.pop_back();
+        } else {
+          CAPSB_CUDA(cudaEventCreate(&done));
+        }
+        CAPSB_CUDA(cudaEventRecord(done, st));
+        CAPSB_CUDA(cudaStreamWaitEvent(eng.copy_stream, done, 0));
+        eng.events.push_back(done);
+        // on the copy stream, behind the ranges' copies: the later write wins
+        const IdxT* pos = deep_pos.get();
+        const IdxT* sa_dev = d_sa;
+        const IdxT* lcp_dev = d_lcp;
+        IdxT* sa_host = static_cast<IdxT*>(eng.sa_sink_dev);
+        IdxT* lcp_host = static_cast<IdxT*>(eng.lcp_sink_dev);
+        launch_map(eng.dev, eng.copy_stream, deep_count, [=] __device__(uint64_t t) {
+          const uint64_t k = pos[t];
+          sa_host[k] = sa_dev[k];
+          lcp_host[k] = lcp_dev[k];
+          // the entry after a group's last member depends on that member as well
+          if (k + 1 < n && (t + 1 == deep_count || static_cast<uint64_t>(pos[t + 1]) != k + 1)) lcp_host[k + 1] = lcp_dev[k + 1];
+        });
+        CAPSB_CUDA(cudaStreamSynchronize(eng.copy_stream));  // deep_pos is released on return
+      }
+      eng.results_streamed = true;
+    }
+  }
+  clock.mark();  // end
 
-  clock.mark();  // 6
   CAPSB_CUDA(cudaStreamSynchronize(st));
+  // marks: 0 begin, 1 packed, 2 partitioned, then per range (begin, sorted, shallow done), then deep done, end
+  const size_t base = 3;
+  for (size_t r = 0; r < range_count; ++r) {
+    ms_local += clock.between(base + 3 * r, base + 3 * r + 1);
+    ms_shallow += clock.between(base + 3 * r + 1, base + 3 * r + 2);
+  }
+  const size_t after = base + 3 * range_count;
   eng.stats.ms_pack = clock.between(0, 1);
-  eng.stats.ms_sort = clock.between(1, 2);
-  eng.stats.ms_heads = clock.between(2, 3);
-  eng.stats.ms_refine = clock.between(3, 4);
-  eng.stats.ms_deep_lcp = clock.between(4, 5);
-  eng.stats.ms_total = clock.between(0, 6);
+  eng.stats.ms_sort = clock.between(1, 2) + ms_local;
+  eng.stats.ms_heads = 0;
+  eng.stats.ms_refine = ms_shallow + clock.between(after - 1, after);
+  eng.stats.ms_deep_lcp = clock.between(after, after + 1);
+  eng.stats.ms_total = clock.between(0, after + 1);
   eng.stats.kernel_launches = g_kernel_launches.load() - launches_before;
   if (eng.radix.timer.enabled) {
     eng.stats.scatter_bytes = eng.radix.timer.bytes;

@@ -204,10 +204,21 @@ CASES = {
 }
 
 
+_case_cache = {}
+
+
+def case_with_oracle(synth, case):
+    """(text, SA, LCP) of a CASES entry; the oracle runs once per case and session."""
+    if case not in _case_cache:
+        text, p = CASES[case](synth)
+        want_sa, want_lcp = oracle_sa_lcp(text, p)
+        _case_cache[case] = (text, want_sa, want_lcp)
+    return _case_cache[case]
+
+
 @pytest.mark.parametrize("case", sorted(CASES))
 def test_matches_oracle(pkg, engine, synth, case):
-    text, p = CASES[case](synth)
-    want_sa, want_lcp = oracle_sa_lcp(text, p)
+    text, want_sa, want_lcp = case_with_oracle(synth, case)
     sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
     assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
     assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
@@ -217,10 +228,31 @@ def test_matches_oracle(pkg, engine, synth, case):
 def test_matches_oracle_with_lsd_key_sort(pkg, engine, synth, case, monkeypatch):
     """CAPSB_SORT=lsd: the key sort of the 64-bit-index path (stable LSD passes) under 32-bit indices."""
     monkeypatch.setenv("CAPSB_SORT", "lsd")
-    text, p = CASES[case](synth)
-    want_sa, want_lcp = oracle_sa_lcp(text, p)
+    text, want_sa, want_lcp = case_with_oracle(synth, case)
     sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
     assert stats["msd_a_bits"] == 0
+    assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
+    assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("ranges", [2, 7, 64])
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_matches_oracle_range_by_range(pkg, engine, synth, case, ranges, pinned, monkeypatch):
+    """CAPSB_STREAM_RANGES=k: the single-GPU path finishes the suffix array k ranges of positions one
+    after the other (what it does by itself for multi-Gbp texts).  With pinned result arrays every
+    finished range is copied to the host while the next one is refined and the deep ties are
+    patched in at the end; with pageable arrays the ranges are still processed one by one but the
+    arrays are copied once."""
+    monkeypatch.setenv("CAPSB_STREAM_RANGES", str(ranges))
+    text, want_sa, want_lcp = case_with_oracle(synth, case)
+    if pinned:
+        sa, lcp, stats = gpu_sa_lcp(pkg, engine, text)
+    else:
+        sa = np.empty(len(text), dtype=np.uint32)
+        lcp = np.empty(len(text), dtype=np.uint32)
+        engine.construct(text, sa, lcp)
+        stats = engine.stats()
     assert np.array_equal(sa, want_sa), f"SA differs ({stats})"
     assert np.array_equal(lcp, want_lcp), f"LCP differs ({stats})"
 
