@@ -72,6 +72,29 @@ struct MsdRecordSource {
   }
 };
 
+// The 64-bit text windows of kMsdItems consecutive suffixes from the (at most four) packed words
+// w[] they span; the first window starts o0 < 64 bits into w[0].  Window t + 1 is window t shifted
+// by one symbol with the next symbol of the text shifted in, so after three runtime shifts
+// everything is shifts by constants.
+template <int kLog2Bits>
+__device__ __forceinline__ void msd_roll_windows(const uint64_t (&w)[4], unsigned o0, uint64_t (&win)[kMsdItems]) {
+  constexpr unsigned kBits = 1u << kLog2Bits;
+  static_assert(kMsdItems * kBits <= 128, "the symbols shifted in come from two tail words");
+  const uint64_t cur0 = o0 ? (w[0] << o0) | (w[1] >> (64u - o0)) : w[0];
+  const uint64_t tail0 = o0 ? (w[1] << o0) | (w[2] >> (64u - o0)) : w[1];  // the 64 bits after cur0
+  const uint64_t tail1 = o0 ? (w[2] << o0) | (w[3] >> (64u - o0)) : w[2];  // and the 64 after those
+  uint64_t cur = cur0;
+#pragma unroll
+  for (int t = 0; t < kMsdItems; ++t) {
+    win[t] = cur;
+    constexpr uint64_t kSymMask = (1ull << kBits) - 1ull;
+    const unsigned at = static_cast<unsigned>(t) * kBits;  // bit offset of the next symbol in the tail
+    const uint64_t tail = at < 64u ? tail0 : tail1;
+    const uint64_t sym = (tail >> (64u - kBits - (at & 63u))) & kSymMask;
+    cur = (cur << kBits) | sym;
+  }
+}
+
 template <class First, class = void>
 struct MsdIsSequentialText : std::false_type {};
 template <class First>
@@ -108,16 +131,18 @@ struct MsdFirstSource {
 #pragma unroll
       for (int q = 0; q < 4; ++q) w[q] = (e0 < valid && w0 + q < nwords) ? __ldg(pt.words + w0 + q) : 0ull;
       const unsigned o0 = static_cast<unsigned>(bit0 & 63u);
+      uint64_t win[kMsdItems];
+      switch (pt.log2_bits) {  // constant shifts per symbol width
+        case 0: msd_roll_windows<0>(w, o0, win); break;
+        case 1: msd_roll_windows<1>(w, o0, win); break;
+        case 2: msd_roll_windows<2>(w, o0, win); break;
+        default: msd_roll_windows<3>(w, o0, win); break;
+      }
 #pragma unroll
       for (int t = 0; t < kMsdItems; ++t) {
-        const unsigned o = o0 + static_cast<unsigned>(t) * bits;  // < 64 + 11 * 8 = 152
-        const unsigned q = o >> 6, r = o & 63u;
-        const uint64_t hi = q == 0 ? w[0] : (q == 1 ? w[1] : w[2]);
-        const uint64_t lo = q == 0 ? w[1] : (q == 1 ? w[2] : w[3]);
-        const uint64_t win = r ? (hi << r) | (lo >> (64u - r)) : hi;
         rec[t] = 0;
         d[t] = bins;
-        if (e0 + t < valid) split(win & first.mask, p0 + t, rec[t], d[t]);
+        if (e0 + t < valid) split(win[t] & first.mask, p0 + t, rec[t], d[t]);
       }
     } else {
 #pragma unroll
@@ -463,19 +488,21 @@ struct MsdLocalSmem {
 };
 
 // Counting pass over records held in registers (rec[t] for the elements e = t * threads + tid <
-// count of the range [base, base + count) of the staging area): ranks, scan of `bins` counters
-// (bins <= 4096), records written back sorted by the digit at `shift`.  start[] holds the digit
-// starts (relative to base) afterwards, start[bins] = count.  All threads of the CTA call it.
-__device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)[kMsdItems], unsigned base,
-                                               unsigned count, unsigned shift, unsigned bits) {
+// count of the range [base, base + count) of the staging area, count <= kN * threads): ranks, scan
+// of `bins` counters (bins <= 4096), records written back sorted by the digit at `shift`.
+// start[] holds the digit starts (relative to base) afterwards, start[bins] = count.  All threads
+// of the CTA call it.
+template <int kN>
+__device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)[kN], unsigned base, unsigned count,
+                                               unsigned shift, unsigned bits) {
   const unsigned tid = threadIdx.x, lane = tid & 31u;
   const unsigned lt = lanemask_lt();
   const unsigned bins = 1u << bits, mask = bins - 1u;
-  unsigned rk[(kMsdItems + 1) / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
+  unsigned rk[(kN + 1) / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
   const bool has0 = tid < count;
   const bool aggregate = msd_probe(has0 ? (static_cast<unsigned>(rec[0] >> shift) & mask) : bins, has0);
 #pragma unroll
-  for (int t = 0; t < kMsdItems; ++t) {
+  for (int t = 0; t < kN; ++t) {
     const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
     const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
     const unsigned r = msd_count(sm.cnt, msd_pad(d), d != bins, aggregate, lane, lt);
@@ -511,7 +538,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
   }
   __syncthreads();
 #pragma unroll
-  for (int t = 0; t < kMsdItems; ++t) {
+  for (int t = 0; t < kN; ++t) {
     const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
     if (e < count) {
       const unsigned d = static_cast<unsigned>(rec[t] >> shift) & mask;
@@ -519,6 +546,98 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
     }
   }
   __syncthreads();
+}
+
+// One bucket of at most kN * threads records (the kernel picks kN by the bucket's size: most
+// buckets of a multi-Gbp text hold about 3000 records, half of what the staging area takes, and
+// the unrolled per-record code of the full size would be half idle on them).
+template <int kN>
+__device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __restrict__ recs,
+                                                 uint32_t* __restrict__ sa_out, uint32_t q, uint32_t beg, uint32_t count,
+                                                 unsigned rem_bits, unsigned key_shift) {
+  const unsigned tid = threadIdx.x;
+  // The first counting pass takes the top hb of the remaining bits: about one counter per two
+  // records (the scan of the counters is per-bucket overhead), at least rem_bits - 12 so that
+  // one more pass can finish a large group, at most 12.
+  unsigned hb = count > 4 ? 31u - static_cast<unsigned>(__clz(count - 1u)) : 1u;  // smallest hb with 2^(hb+1) >= count
+  if (hb > static_cast<unsigned>(kMsdLocalBits)) hb = kMsdLocalBits;
+  if (hb + kMsdLocalBits < rem_bits) hb = rem_bits - kMsdLocalBits;
+  if (hb > rem_bits) hb = rem_bits;
+  const unsigned lb = rem_bits - hb;
+  // the key bits every record of this bucket shares, in place above the remaining ones
+  const uint64_t prefix = static_cast<uint64_t>(q) << rem_bits;
+  const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
+  uint64_t rec[kN];
+#pragma unroll
+  for (int t = 0; t < kN; ++t) {
+    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    rec[t] = e < count ? ld_stream_u64(recs + beg + e) : 0ull;
+  }
+  if (hb > 0 && count > 1) {
+    msd_local_pass<kN>(sm, rec, 0, count, 32u + lb, hb);
+    if (lb == 0) {  // the pass consumed every remaining bit
+      for (unsigned s = tid; s < count; s += kMsdThreads) {
+        const uint64_t r = sm.stage[s];
+        recs[beg + s] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
+        sa_out[beg + s] = static_cast<uint32_t>(r);
+      }
+    } else {
+      // groups = runs of equal top digits, now contiguous.  A record of a small group counts the
+      // records of its group that precede it (by the remaining bits, then by slot) and leaves
+      // for its final place at once: key in place of the records, suffix to the suffix array.
+      // Large groups are listed and get a counting pass of their own.
+      const unsigned hmask = (1u << hb) - 1u;
+#pragma unroll 2
+      for (unsigned s = tid; s < count; s += kMsdThreads) {
+        const uint64_t r = sm.stage[s];
+        const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
+        const unsigned g0 = sm.start[msd_pad(d)], g1 = sm.start[msd_pad(d + 1)];
+        if (g1 - g0 <= kMsdSmallGroup) {
+          const unsigned mine = static_cast<unsigned>(r >> 32);
+          unsigned rank = 0;
+          for (unsigned u = g0; u < g1; ++u) {
+            const unsigned other = static_cast<unsigned>(sm.stage[u] >> 32);
+            rank += (other < mine || (other == mine && u < s)) ? 1u : 0u;
+          }
+          recs[beg + g0 + rank] = (prefix | (static_cast<uint64_t>(mine) & rem_mask)) << key_shift;
+          sa_out[beg + g0 + rank] = static_cast<uint32_t>(r);
+        } else if (s == g0) {
+          sm.big[atomicAdd(&sm.nbig, 1u)] = g0 | ((g1 - g0 - 1u) << 16);  // start, size - 1 < 65536
+        }
+      }
+      __syncthreads();
+      const unsigned nbig = sm.nbig;
+      for (unsigned j = 0; j < nbig; ++j) {
+        const unsigned g0 = sm.big[j] & 0xFFFFu, gsize = (sm.big[j] >> 16) + 1u;
+#pragma unroll
+        for (int t = 0; t < kN; ++t) {
+          const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+          rec[t] = e < gsize ? sm.stage[g0 + e] : 0ull;
+        }
+        __syncthreads();  // every record of the group is in registers before any is written back
+        msd_local_pass<kN>(sm, rec, g0, gsize, 32u, lb);
+        for (unsigned e = tid; e < gsize; e += kMsdThreads) {
+          const uint64_t r = sm.stage[g0 + e];
+          recs[beg + g0 + e] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
+          sa_out[beg + g0 + e] = static_cast<uint32_t>(r);
+        }
+      }
+      if (nbig > 0) {
+        __syncthreads();
+        if (tid == 0) sm.nbig = 0;
+      }
+    }
+    __syncthreads();  // the staging area is refilled by the next bucket
+  } else {
+#pragma unroll
+    for (int t = 0; t < kN; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      if (e < count) {
+        recs[beg + e] = (prefix | ((rec[t] >> 32) & rem_mask)) << key_shift;
+        sa_out[beg + e] = static_cast<uint32_t>(rec[t]);
+      }
+    }
+  }
 }
 
 static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_local_kernel(uint64_t* __restrict__ recs,
@@ -532,6 +651,7 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
   const unsigned tid = threadIdx.x;
   const unsigned rem_bits = key_bits - prefix_bits;  // <= 24
   const unsigned key_shift = 64u - key_bits;
+  constexpr int kHalf = (kMsdItems + 1) / 2;
   for (unsigned b = tid; b < static_cast<unsigned>(kMsdLocalPadded); b += kMsdThreads) sm.cnt[b] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
@@ -543,88 +663,10 @@ static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_lo
       if (tid == 0) large_list[atomicAdd(large_count, 1u)] = q;
       continue;
     }
-    // The first counting pass takes the top hb of the remaining bits: about one counter per two
-    // records (the scan of the counters is per-bucket overhead), at least rem_bits - 12 so that
-    // one more pass can finish a large group, at most 12.
-    unsigned hb = count > 4 ? 31u - static_cast<unsigned>(__clz(count - 1u)) : 1u;  // smallest hb with 2^(hb+1) >= count
-    if (hb > static_cast<unsigned>(kMsdLocalBits)) hb = kMsdLocalBits;
-    if (hb + kMsdLocalBits < rem_bits) hb = rem_bits - kMsdLocalBits;
-    if (hb > rem_bits) hb = rem_bits;
-    const unsigned lb = rem_bits - hb;
-    // the key bits every record of this bucket shares, in place above the remaining ones
-    const uint64_t prefix = static_cast<uint64_t>(q) << rem_bits;
-    const uint64_t rem_mask = (1ull << rem_bits) - 1ull;
-    uint64_t rec[kMsdItems];
-#pragma unroll
-    for (int t = 0; t < kMsdItems; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-      rec[t] = e < count ? ld_stream_u64(recs + beg + e) : 0ull;
-    }
-    if (hb > 0 && count > 1) {
-      msd_local_pass(sm, rec, 0, count, 32u + lb, hb);
-      if (lb == 0) {  // the pass consumed every remaining bit
-        for (unsigned s = tid; s < count; s += kMsdThreads) {
-          const uint64_t r = sm.stage[s];
-          recs[beg + s] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
-          sa_out[beg + s] = static_cast<uint32_t>(r);
-        }
-      } else {
-        // groups = runs of equal top digits, now contiguous.  A record of a small group counts the
-        // records of its group that precede it (by the remaining bits, then by slot) and leaves
-        // for its final place at once: key in place of the records, suffix to the suffix array.
-        // Large groups are listed and get a counting pass of their own.
-        const unsigned hmask = (1u << hb) - 1u;
-#pragma unroll 4
-        for (unsigned s = tid; s < count; s += kMsdThreads) {
-          const uint64_t r = sm.stage[s];
-          const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
-          const unsigned g0 = sm.start[msd_pad(d)], g1 = sm.start[msd_pad(d + 1)];
-          if (g1 - g0 <= kMsdSmallGroup) {
-            const unsigned mine = static_cast<unsigned>(r >> 32);
-            unsigned rank = 0;
-            for (unsigned u = g0; u < g1; ++u) {
-              const unsigned other = static_cast<unsigned>(sm.stage[u] >> 32);
-              rank += (other < mine || (other == mine && u < s)) ? 1u : 0u;
-            }
-            recs[beg + g0 + rank] = (prefix | (static_cast<uint64_t>(mine) & rem_mask)) << key_shift;
-            sa_out[beg + g0 + rank] = static_cast<uint32_t>(r);
-          } else if (s == g0) {
-            sm.big[atomicAdd(&sm.nbig, 1u)] = g0 | ((g1 - g0 - 1u) << 16);  // start, size - 1 < 65536
-          }
-        }
-        __syncthreads();
-        const unsigned nbig = sm.nbig;
-        for (unsigned j = 0; j < nbig; ++j) {
-          const unsigned g0 = sm.big[j] & 0xFFFFu, gsize = (sm.big[j] >> 16) + 1u;
-#pragma unroll
-          for (int t = 0; t < kMsdItems; ++t) {
-            const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-            rec[t] = e < gsize ? sm.stage[g0 + e] : 0ull;
-          }
-          __syncthreads();  // every record of the group is in registers before any is written back
-          msd_local_pass(sm, rec, g0, gsize, 32u, lb);
-          for (unsigned e = tid; e < gsize; e += kMsdThreads) {
-            const uint64_t r = sm.stage[g0 + e];
-            recs[beg + g0 + e] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
-            sa_out[beg + g0 + e] = static_cast<uint32_t>(r);
-          }
-        }
-        if (nbig > 0) {
-          __syncthreads();
-          if (tid == 0) sm.nbig = 0;
-        }
-      }
-      __syncthreads();  // the staging area is refilled by the next bucket
-    } else {
-#pragma unroll
-      for (int t = 0; t < kMsdItems; ++t) {
-        const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
-        if (e < count) {
-          recs[beg + e] = (prefix | ((rec[t] >> 32) & rem_mask)) << key_shift;
-          sa_out[beg + e] = static_cast<uint32_t>(rec[t]);
-        }
-      }
-    }
+    if (count <= static_cast<uint32_t>(kHalf * kMsdThreads))
+      msd_local_bucket<kHalf>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
+    else
+      msd_local_bucket<kMsdItems>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
   }
 }
 

@@ -320,6 +320,77 @@ struct SuffixListSource {
   static constexpr uint64_t bytes_read_per_item() { return 2 * sizeof(IdxT) + 1; }
 };
 
+// Rank (= final position in the sorted bucket keys[0, count) / sa[0, count)) of a suffix j that holds
+// no published rank.  Only the suffixes that are still tied when the prefix doubling starts publish
+// ranks; every other suffix is final, and its position can be found:
+//   * its key is unique: the position of the key (binary search);
+//   * the text rounds separated it from every other suffix within its first `depth` symbols: inside
+//     its key group — sorted by now, except for the still-tied subgroups, whose members all compare
+//     the same way against j — a binary search that compares text from the end of the key on;
+//   * the pair-chain step ordered it against the one suffix it was tied with: the two are
+//     neighbours, so the search ends next to it.
+// (Publishing those ranks instead is a random 4-byte scatter over the whole text: 15 of the 100 ms the
+// refinement took at 3.1 Gbp, and an all-to-all in the sharded path.)
+template <class IdxT>
+__device__ __forceinline__ uint64_t rank_of_unpublished(const PackedText& pt, const uint64_t* __restrict__ keys,
+                                                        const IdxT* __restrict__ sa, uint64_t count, uint64_t want,
+                                                        uint64_t j, uint64_t key_symbols, uint64_t depth) {
+  uint64_t lo = 0, hi = count;
+  while (lo < hi) {  // first position whose key is >= want
+    const uint64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < want)
+      lo = mid + 1;
+    else
+      hi = mid;
+  }
+  const uint64_t g0 = lo;
+  if (g0 + 1 >= count || keys[g0 + 1] != want) return g0;  // the key is unique
+  uint64_t g1 = g0 + 2;
+  {  // end of the key group: gallop, then bisect
+    uint64_t step = 2;
+    while (g1 < count && keys[g1] == want) {
+      g1 += step;
+      step <<= 1;
+    }
+    uint64_t a = g1 - (step >> 1), b = g1 < count ? g1 : count;  // keys[a] == want (or a == g0 + 1), keys[b] != want
+    if (a < g0 + 1) a = g0 + 1;
+    while (b - a > 1) {
+      const uint64_t mid = (a + b) >> 1;
+      if (keys[mid] == want)
+        a = mid;
+      else
+        b = mid;
+    }
+    g1 = b;
+  }
+  const unsigned spw = pt.syms_per_word();
+  const unsigned limit = static_cast<unsigned>((depth > key_symbols ? depth - key_symbols : 0) / spw) + 2u;
+  uint64_t a = g0, b = g1;
+  while (a < b) {
+    const uint64_t mid = (a + b) >> 1;
+    const uint64_t s = sa[mid];
+    if (s == j) return mid;
+    uint64_t l = 0;
+    const bool decided = pt.common_prefix(j, s, key_symbols, limit, &l);
+    if (!decided) {  // equal beyond `depth` symbols: j's pair partner (or a group j is next to): look around
+      for (uint64_t r = 1; r < g1 - g0; ++r) {
+        if (mid >= g0 + r && sa[mid - r] == j) return mid - r;
+        if (mid + r < g1 && sa[mid + r] == j) return mid + r;
+      }
+      return g0;  // not reached: j is in its key group
+    }
+    const uint64_t shorter = pt.n - (j > s ? j : s);
+    const bool j_first = l >= shorter ? j > s : pt.symbol(j + l) < pt.symbol(s + l);
+    if (j_first)
+      b = mid;
+    else
+      a = mid + 1;
+  }
+  for (uint64_t k = g0; k < g1; ++k)  // not reached (kept so that a wrong assumption costs time, not correctness)
+    if (sa[k] == j) return k;
+  return g0;
+}
+
 // ---------------------------------------------------------------------------------------
 // Rank storage of the single-GPU path: isa[text position] = first SA position of the
 // suffix's current group — but only for suffixes that were ever tied.  A suffix whose key is
@@ -339,9 +410,14 @@ struct LocalRanks {
   PackedText pt;
   const uint64_t* keys;  // sorted (masked) keys of all n suffixes
   uint64_t key_mask;
+  const IdxT* sa;             // the suffix array under construction (all n positions)
+  uint64_t key_symbols;       // symbols the key covers
+  uint64_t resolved_depth = 0;  // symbols within which every final suffix differs from all others (set by refine_deep)
+  static constexpr bool kPublishesAllTied = false;  // ranks of final suffixes are found, not published (rank_of_unpublished)
   DevBuf<IdxT> isa;  // allocated when the refinement first needs ranks (reset)
-  LocalRanks(Engine& e, uint64_t n_, const PackedText& pt_, const uint64_t* keys_, uint64_t key_mask_)
-      : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_) {}
+  LocalRanks(Engine& e, uint64_t n_, const PackedText& pt_, const uint64_t* keys_, uint64_t key_mask_, const IdxT* sa_,
+             uint64_t key_symbols_)
+      : eng(e), n(n_), pt(pt_), keys(keys_), key_mask(key_mask_), sa(sa_), key_symbols(key_symbols_) {}
 
   uint64_t global_sum(uint64_t v) { return v; }  // over the ranks of the construction
 
@@ -371,26 +447,16 @@ struct LocalRanks {
     const PackedText text = pt;
     const uint64_t* sorted_keys = keys;
     const uint64_t mask = key_mask;
+    const IdxT* d_sa = sa;
+    const uint64_t ksym = key_symbols, depth = resolved_depth;
     launch_map(eng.dev, eng.stream, m, [=] __device__(uint64_t t) {
       const uint64_t i = idx[t];
       const uint64_t ih = i + h;
       uint64_t second = n_ - 1 - i;
       if (ih < n_) {
         const IdxT r = d_isa[ih];
-        if (r != kUnset) {
-          second = r;
-        } else {  // never tied: the position of its (unique) key among the sorted keys
-          const uint64_t want = text.window(ih) & mask;
-          uint64_t lo = 0, hi = n_;
-          while (lo < hi) {
-            const uint64_t mid = (lo + hi) >> 1;
-            if (sorted_keys[mid] < want)
-              lo = mid + 1;
-            else
-              hi = mid;
-          }
-          second = lo;
-        }
+        second = r != kUnset ? static_cast<uint64_t>(r)  // still tied when the doubling started: its group head
+                             : rank_of_unpublished<IdxT>(text, sorted_keys, d_sa, n_, text.window(ih) & mask, ih, ksym, depth);
       }
       second_out[t] = static_cast<IdxT>(second);
     });
@@ -1070,6 +1136,8 @@ template <class IdxT>
 struct RefineState {
   ActiveList<IdxT> act;
   uint64_t h = 0;             // symbols every group of act agrees on
+  uint64_t h_resolved = 0;    // symbols within which every suffix that left the list differs from all others
+                              // (pairs ordered by the pair-chain step excepted); >= h
   uint64_t total_active = 0;  // over the ranks of the construction
 };
 
@@ -1222,6 +1290,7 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
     if (total_active > 0 && total_active * 4 > before * 3) break;
   }
   state.h = h;
+  state.h_resolved = h;
   state.total_active = total_active;
 }
 
@@ -1252,7 +1321,8 @@ void refine_deep(Engine& eng, Ranks& ranks, IdxT* d_sa, IdxT* d_lcp, uint64_t po
   };
   if (trace) round_start = std::chrono::steady_clock::now();
   ranks.reset();
-  {  // every ever-tied suffix publishes its SA position; the still-tied ones then their group head
+  ranks.resolved_depth = state.h_resolved;
+  if (Ranks::kPublishesAllTied) {  // every ever-tied suffix publishes its SA position; the still-tied ones then their group head
     const IdxT* p0 = tied.pos.get();
     DevBuf<IdxT> all_idx(tied.m, st), all_pos(tied.m, st);
     IdxT* ai = all_idx.get();

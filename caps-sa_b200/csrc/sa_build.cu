@@ -181,7 +181,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
   float ms_local = 0, ms_shallow = 0;
 
   // ---- 3. ties: per range, the shallow part of the refinement (pair chains + text rounds) ------
-  LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits));
+  LocalRanks<IdxT> ranks(eng, n, pt, keys, key_mask_of(key_bits), d_sa, key_bits >> log2_bits);
   std::vector<TiedSet<IdxT>> tied_of(range_count);
   std::vector<RefineState<IdxT>> state_of(range_count);
   for (size_t r = 0; r < range_count; ++r) {
@@ -219,6 +219,7 @@ void build_sa_lcp(Engine& eng, const uint8_t* d_text, uint64_t n, IdxT* d_sa, Id
     tied.m += tied_of[r].m;
     deep.act.m += state_of[r].act.m;
     if (state_of[r].act.m && state_of[r].h < deep.h) deep.h = state_of[r].h;
+    if (state_of[r].h_resolved > deep.h_resolved) deep.h_resolved = state_of[r].h_resolved;
   }
   deep.total_active = deep.act.m;
   DevBuf<IdxT> deep_pos(deep.act.m, st);  // the positions the deep stages may still change

@@ -121,6 +121,8 @@ template <class IdxT>
 struct ShardedRanks {
   using Comp = typename IdxTraits<IdxT>::Comp;
   static constexpr IdxT kUnset = ~IdxT(0);
+  static constexpr bool kPublishesAllTied = true;  // (final suffixes publish their position when the doubling starts)
+  uint64_t resolved_depth = 0;
   Engine& eng;
   Comm& comm;
   SliceMap map;
