@@ -44,7 +44,8 @@ constexpr int kMsdMaxBits = 10;                    // digit width of levels A an
 constexpr int kMsdMaxBins = 1 << kMsdMaxBits;
 constexpr int kMsdLocalBits = 12;                  // digit width of the counting passes inside a bucket
 constexpr int kMsdLocalBins = 1 << kMsdLocalBits;
-constexpr int kMsdLocalCap = kMsdTile;             // largest bucket the local sort takes
+constexpr int kMsdLocalCap = kMsdTile;             // largest bucket the two-CTAs-per-SM local sort takes
+constexpr int kMsdBigThreads = 1024;               // second instantiation: one CTA per SM, twice the bucket
 constexpr unsigned kMsdSmallGroup = 32;            // groups up to this size are ordered by comparison
 static_assert(kMsdTile <= 8192 && kMsdThreads % 32 == 0, "ranks are packed in 13 / 16 bits");
 
@@ -478,12 +479,13 @@ __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_scatter_k
 __device__ __forceinline__ unsigned msd_pad(unsigned b) { return b + (b >> 5); }
 constexpr int kMsdLocalPadded = kMsdLocalBins + kMsdLocalBins / 32 + 2;
 
+template <int kCap>
 struct MsdLocalSmem {
-  uint64_t stage[kMsdLocalCap];
+  uint64_t stage[kCap];
   unsigned cnt[kMsdLocalPadded];
   unsigned start[kMsdLocalPadded];
   unsigned warp_tot[32];
-  unsigned big[kMsdLocalCap / (kMsdSmallGroup + 1) + 1];  // digits of the groups too large for comparison ordering
+  unsigned big[kCap / (kMsdSmallGroup + 1) + 1];  // (start, size - 1) of the groups too large for comparison ordering
   unsigned nbig;
 };
 
@@ -492,8 +494,8 @@ struct MsdLocalSmem {
 // of `bins` counters (bins <= 4096), records written back sorted by the digit at `shift`.
 // start[] holds the digit starts (relative to base) afterwards, start[bins] = count.  All threads
 // of the CTA call it.
-template <int kN>
-__device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)[kN], unsigned base, unsigned count,
+template <int kN, int kT, class Smem>
+__device__ __forceinline__ void msd_local_pass(Smem& sm, uint64_t (&rec)[kN], unsigned base, unsigned count,
                                                unsigned shift, unsigned bits) {
   const unsigned tid = threadIdx.x, lane = tid & 31u;
   const unsigned lt = lanemask_lt();
@@ -503,7 +505,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
   const bool aggregate = msd_probe(has0 ? (static_cast<unsigned>(rec[0] >> shift) & mask) : bins, has0);
 #pragma unroll
   for (int t = 0; t < kN; ++t) {
-    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    const unsigned e = static_cast<unsigned>(t) * kT + tid;
     const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
     const unsigned r = msd_count(sm.cnt, msd_pad(d), d != bins, aggregate, lane, lt);
     if (t & 1)
@@ -513,7 +515,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
   }
   __syncthreads();
   {  // eight consecutive counters per thread
-    constexpr int kPer = (kMsdLocalBins + kMsdThreads - 1) / kMsdThreads;
+    constexpr int kPer = (kMsdLocalBins + kT - 1) / kT;
     unsigned c[kPer], sum = 0;
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
@@ -521,7 +523,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
       c[q] = b < bins ? sm.cnt[msd_pad(b)] : 0u;
       sum += c[q];
     }
-    unsigned run = msd_block_excl_scan<kMsdThreads>(sum, sm.warp_tot);
+    unsigned run = msd_block_excl_scan<kT>(sum, sm.warp_tot);
 #pragma unroll
     for (int q = 0; q < kPer; ++q) {
       const unsigned b = tid * kPer + q;
@@ -539,7 +541,7 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
   __syncthreads();
 #pragma unroll
   for (int t = 0; t < kN; ++t) {
-    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    const unsigned e = static_cast<unsigned>(t) * kT + tid;
     if (e < count) {
       const unsigned d = static_cast<unsigned>(rec[t] >> shift) & mask;
       sm.stage[base + sm.start[msd_pad(d)] + ((rk[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu)] = rec[t];
@@ -551,8 +553,8 @@ __device__ __forceinline__ void msd_local_pass(MsdLocalSmem& sm, uint64_t (&rec)
 // One bucket of at most kN * threads records (the kernel picks kN by the bucket's size: most
 // buckets of a multi-Gbp text hold about 3000 records, half of what the staging area takes, and
 // the unrolled per-record code of the full size would be half idle on them).
-template <int kN>
-__device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __restrict__ recs,
+template <int kN, int kT, class Smem>
+__device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict__ recs,
                                                  uint32_t* __restrict__ sa_out, uint32_t q, uint32_t beg, uint32_t count,
                                                  unsigned rem_bits, unsigned key_shift) {
   const unsigned tid = threadIdx.x;
@@ -570,13 +572,13 @@ __device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __r
   uint64_t rec[kN];
 #pragma unroll
   for (int t = 0; t < kN; ++t) {
-    const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+    const unsigned e = static_cast<unsigned>(t) * kT + tid;
     rec[t] = e < count ? ld_stream_u64(recs + beg + e) : 0ull;
   }
   if (hb > 0 && count > 1) {
-    msd_local_pass<kN>(sm, rec, 0, count, 32u + lb, hb);
+    msd_local_pass<kN, kT>(sm, rec, 0, count, 32u + lb, hb);
     if (lb == 0) {  // the pass consumed every remaining bit
-      for (unsigned s = tid; s < count; s += kMsdThreads) {
+      for (unsigned s = tid; s < count; s += kT) {
         const uint64_t r = sm.stage[s];
         recs[beg + s] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
         sa_out[beg + s] = static_cast<uint32_t>(r);
@@ -588,7 +590,7 @@ __device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __r
       // Large groups are listed and get a counting pass of their own.
       const unsigned hmask = (1u << hb) - 1u;
 #pragma unroll 2
-      for (unsigned s = tid; s < count; s += kMsdThreads) {
+      for (unsigned s = tid; s < count; s += kT) {
         const uint64_t r = sm.stage[s];
         const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
         const unsigned g0 = sm.start[msd_pad(d)], g1 = sm.start[msd_pad(d + 1)];
@@ -611,12 +613,12 @@ __device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __r
         const unsigned g0 = sm.big[j] & 0xFFFFu, gsize = (sm.big[j] >> 16) + 1u;
 #pragma unroll
         for (int t = 0; t < kN; ++t) {
-          const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+          const unsigned e = static_cast<unsigned>(t) * kT + tid;
           rec[t] = e < gsize ? sm.stage[g0 + e] : 0ull;
         }
         __syncthreads();  // every record of the group is in registers before any is written back
-        msd_local_pass<kN>(sm, rec, g0, gsize, 32u, lb);
-        for (unsigned e = tid; e < gsize; e += kMsdThreads) {
+        msd_local_pass<kN, kT>(sm, rec, g0, gsize, 32u, lb);
+        for (unsigned e = tid; e < gsize; e += kT) {
           const uint64_t r = sm.stage[g0 + e];
           recs[beg + g0 + e] = (prefix | ((r >> 32) & rem_mask)) << key_shift;
           sa_out[beg + g0 + e] = static_cast<uint32_t>(r);
@@ -631,7 +633,7 @@ __device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __r
   } else {
 #pragma unroll
     for (int t = 0; t < kN; ++t) {
-      const unsigned e = static_cast<unsigned>(t) * kMsdThreads + tid;
+      const unsigned e = static_cast<unsigned>(t) * kT + tid;
       if (e < count) {
         recs[beg + e] = (prefix | ((rec[t] >> 32) & rem_mask)) << key_shift;
         sa_out[beg + e] = static_cast<uint32_t>(rec[t]);
@@ -640,33 +642,41 @@ __device__ __forceinline__ void msd_local_bucket(MsdLocalSmem& sm, uint64_t* __r
   }
 }
 
-static __global__ void __launch_bounds__(kMsdThreads, CAPSB_MSD_MIN_CTAS) msd_local_kernel(uint64_t* __restrict__ recs,
-                                                                  const uint32_t* __restrict__ child_start,
-                                                                  uint32_t q_begin, uint32_t q_end, unsigned key_bits,
-                                                                  unsigned prefix_bits, uint32_t* __restrict__ sa_out,
-                                                                  uint32_t* __restrict__ large_list,
-                                                                  uint32_t* __restrict__ large_count) {
+// kT threads take buckets of up to kT * kMsdItems records.  Two instantiations: 512 threads, two CTAs
+// per SM, over a range of bucket numbers; and 1024 threads, one CTA per SM, over the list of buckets the
+// first one found too large (repeat families: 10-mers shared by thousands of copies).  Buckets too
+// large for this instantiation are appended to large_list.
+template <int kT, int kMinCtas>
+__global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __restrict__ recs,
+                                                                 const uint32_t* __restrict__ child_start,
+                                                                 const uint32_t* __restrict__ bucket_list,
+                                                                 uint32_t q_begin, uint32_t q_end, unsigned key_bits,
+                                                                 unsigned prefix_bits, uint32_t* __restrict__ sa_out,
+                                                                 uint32_t* __restrict__ large_list,
+                                                                 uint32_t* __restrict__ large_count) {
   extern __shared__ __align__(16) unsigned char msd_smem_raw[];
-  MsdLocalSmem& sm = *reinterpret_cast<MsdLocalSmem*>(msd_smem_raw);
+  using Smem = MsdLocalSmem<kT * kMsdItems>;
+  Smem& sm = *reinterpret_cast<Smem*>(msd_smem_raw);
   const unsigned tid = threadIdx.x;
   const unsigned rem_bits = key_bits - prefix_bits;  // <= 24
   const unsigned key_shift = 64u - key_bits;
   constexpr int kHalf = (kMsdItems + 1) / 2;
-  for (unsigned b = tid; b < static_cast<unsigned>(kMsdLocalPadded); b += kMsdThreads) sm.cnt[b] = 0;
+  for (unsigned b = tid; b < static_cast<unsigned>(kMsdLocalPadded); b += kT) sm.cnt[b] = 0;
   if (tid == 0) sm.nbig = 0;
   __syncthreads();
-  for (uint32_t q = q_begin + blockIdx.x; q < q_end; q += gridDim.x) {
+  for (uint32_t at = q_begin + blockIdx.x; at < q_end; at += gridDim.x) {
+    const uint32_t q = bucket_list ? bucket_list[at] : at;
     const uint32_t beg = child_start[q];
     const uint32_t count = child_start[q + 1] - beg;
     if (count == 0) continue;
-    if (count > static_cast<uint32_t>(kMsdLocalCap)) {
+    if (count > static_cast<uint32_t>(kT * kMsdItems)) {
       if (tid == 0) large_list[atomicAdd(large_count, 1u)] = q;
       continue;
     }
-    if (count <= static_cast<uint32_t>(kHalf * kMsdThreads))
-      msd_local_bucket<kHalf>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
+    if (count <= static_cast<uint32_t>(kHalf * kT))
+      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
     else
-      msd_local_bucket<kMsdItems>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
+      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
   }
 }
 

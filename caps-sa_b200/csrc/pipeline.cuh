@@ -190,7 +190,8 @@ struct MsdSorted {
   uint32_t nbuckets = 0;
   DevBuf<uint32_t> start_b;        // nbuckets + 1 bucket starts
   std::vector<uint32_t> a_starts;  // host copy of the 2^a + 1 level-A bucket starts (on request)
-  DevBuf<uint32_t> large_list, large_count;
+  DevBuf<uint32_t> large_list, large_count;  // two lists (oversized for the first / the second local kernel), two counts
+  uint64_t large_capacity = 0;
 };
 
 template <class FirstSrc>
@@ -228,8 +229,9 @@ void msd_partition(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bit
     ms.a_starts.resize((1u << a) + 1);
     read_back(st, ms.a_starts.data(), start_a.get(), ms.a_starts.size() * sizeof(uint32_t));
   }
-  ms.large_list.alloc(count / kMsdLocalCap + 1, st);
-  ms.large_count.alloc(1, st);
+  ms.large_capacity = count / kMsdLocalCap + 1;
+  ms.large_list.alloc(2 * ms.large_capacity, st);
+  ms.large_count.alloc(2, st);
 }
 
 inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint32_t* sa_out, uint32_t q_begin,
@@ -237,22 +239,36 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
   cudaStream_t st = eng.stream;
   const DeviceInfo& dev = eng.dev;
   if (q_begin >= q_end) return;
-  CAPSB_CUDA(cudaMemsetAsync(ms.large_count.get(), 0, sizeof(uint32_t), st));
+  uint32_t* counts = ms.large_count.get();  // [0] buckets too large for the first kernel, [1] for the second
+  CAPSB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint32_t), st));
+  uint32_t* huge_list = ms.large_list.get() + ms.large_capacity;
   {
-    constexpr size_t kSmem = sizeof(MsdLocalSmem);
-    msd_allow_smem(msd_local_kernel, kSmem);
+    using Small = MsdLocalSmem<kMsdLocalCap>;
+    msd_allow_smem(msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>, sizeof(Small));
     const uint32_t grid = std::min<uint32_t>(q_end - q_begin, static_cast<uint32_t>(dev.sm_count) * 2u);
     MsdTimed timed(eng.msd_timers.local, st, records * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
-    CAPSB_LAUNCH(msd_local_kernel, grid, kMsdThreads, kSmem, st, keys_out, ms.start_b.get(), q_begin, q_end,
-                 ms.key_bits, ms.a + ms.b, sa_out, ms.large_list.get(), ms.large_count.get());
+    CAPSB_LAUNCH((msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>), grid, kMsdThreads, sizeof(Small), st, keys_out,
+                 ms.start_b.get(), static_cast<const uint32_t*>(nullptr), q_begin, q_end, ms.key_bits, ms.a + ms.b,
+                 sa_out, ms.large_list.get(), counts);
   }
   uint32_t nlarge = 0;
-  read_back(st, &nlarge, ms.large_count.get(), sizeof(uint32_t));
-  eng.stats.msd_large_buckets += nlarge;
-  if (nlarge > 0) {
+  read_back(st, &nlarge, counts, sizeof(uint32_t));
+  if (nlarge == 0) return;
+  {  // the listed buckets with twice the threads and staging area, one CTA per SM
+    using Big = MsdLocalSmem<kMsdBigThreads * kMsdItems>;
+    msd_allow_smem(msd_local_kernel<kMsdBigThreads, 1>, sizeof(Big));
+    const uint32_t grid = std::min<uint32_t>(nlarge, static_cast<uint32_t>(dev.sm_count));
+    CAPSB_LAUNCH((msd_local_kernel<kMsdBigThreads, 1>), grid, kMsdBigThreads, sizeof(Big), st, keys_out,
+                 ms.start_b.get(), static_cast<const uint32_t*>(ms.large_list.get()), 0u, nlarge, ms.key_bits,
+                 ms.a + ms.b, sa_out, huge_list, counts + 1);
+  }
+  uint32_t nhuge = 0;
+  read_back(st, &nhuge, counts + 1, sizeof(uint32_t));
+  eng.stats.msd_large_buckets += nhuge;
+  if (nhuge > 0) {
     uint64_t large_records = 0;
-    msd_sort_large_buckets(dev, st, eng.radix, keys_out, sa_out, ms.start_b.get(), ms.large_list.get(), nlarge,
-                           ms.key_bits, ms.a + ms.b, eng.scan32, &large_records);
+    msd_sort_large_buckets(dev, st, eng.radix, keys_out, sa_out, ms.start_b.get(), huge_list, nhuge, ms.key_bits,
+                           ms.a + ms.b, eng.scan32, &large_records);
     eng.stats.msd_large_records += large_records;
   }
 }

@@ -42,6 +42,10 @@ void caps_port_map_acgt(char* text, uint64_t n);
 int caps_check_sa_lcp(const char* text, uint64_t n, const void* sa, const void* lcp,
                       int idx_bytes, uint64_t* bad_pos);
 
+/* Number of OpenMP threads the multi-threaded checkers use from now on (launchers like torchrun
+ * export OMP_NUM_THREADS=1). */
+void caps_oracle_set_threads(int threads);
+
 /* caps_check_sa_lcp with OpenMP loops (Kasai's walk restarted per range of text positions) and
  * an inverse permutation at the input's index width: the form bench.py applies to the 3.1 G
  * suffix results.  Same codes. */

@@ -11,6 +11,20 @@
 
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Launchers such as torchrun export OMP_NUM_THREADS=1 to every rank; the multi-threaded checkers
+ * below would then crawl on one core (3.1 G suffixes: ten minutes instead of 25 s).  The caller
+ * says how many threads the checker may use. */
+void caps_oracle_set_threads(int threads) {
+#ifdef _OPENMP
+  if (threads > 0) omp_set_num_threads(threads);
+#else
+  (void)threads;
+#endif
+}
 
 static inline uint64_t get_idx(const void* arr, int w, uint64_t k) {
   return w == 4 ? (uint64_t)((const uint32_t*)arr)[k] : ((const uint64_t*)arr)[k];

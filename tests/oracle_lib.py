@@ -48,6 +48,8 @@ def port():
         lib.caps_port_map_acgt.restype = None
         lib.caps_check_sa_lcp.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp.restype = C.c_int
+        lib.caps_oracle_set_threads.argtypes = [C.c_int]
+        lib.caps_oracle_set_threads.restype = None
         lib.caps_check_sa_lcp_mt.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp_mt.restype = C.c_int
         lib.caps_check_sa_lcp_periodic.argtypes = [p, u64, u64, p, p, C.c_int, C.POINTER(u64)]
@@ -136,6 +138,8 @@ def check_sa_lcp_mt(text, sa: np.ndarray, lcp: np.ndarray):
     assert sa.flags.c_contiguous and lcp.flags.c_contiguous
     assert sa.dtype == lcp.dtype and sa.dtype in (np.uint32, np.uint64)
     bad = C.c_uint64(0)
+    # all the cores this process may run on, whatever OMP_NUM_THREADS the launcher exported
+    port().caps_oracle_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     rc = port().caps_check_sa_lcp_mt(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
                                      sa.dtype.itemsize, C.byref(bad))
     return rc, bad.value
