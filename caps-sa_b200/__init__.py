@@ -36,6 +36,7 @@ EXPORTED_SYMBOLS = [
     "caps_sa_gpu_engine_comm_init", "caps_sa_gpu_construct_sharded_device_u32",
     "caps_sa_gpu_construct_sharded_device_u64", "caps_sa_gpu_construct_sharded_u32",
     "caps_sa_gpu_construct_sharded_u64", "caps_sa_gpu_shard_copy", "caps_sa_gpu_stage_key_sort_u32",
+    "caps_sa_gpu_set_cli_byte_mapping",
 ]
 COMM_ID_BYTES = 128
 
@@ -102,6 +103,8 @@ def lib():
         L.caps_sa_gpu_stage_radix_sort_u64_u32.argtypes = [p, p, p, u64, C.c_uint, C.c_uint]
         L.caps_sa_gpu_stage_scan_u32.argtypes = [p, p, u64, i32]
         L.caps_sa_gpu_stage_key_sort_u32.argtypes = [p, p, u64, i32, p, p]
+        L.caps_sa_gpu_set_cli_byte_mapping.argtypes = [i32]
+        L.caps_sa_gpu_set_cli_byte_mapping.restype = i32
         for name in ("caps_sa_gpu_construct_multi_u32", "caps_sa_gpu_construct_multi_u64"):
             getattr(L, name).argtypes = [C.POINTER(i32), i32, p, u64, p, p, u64, u64, C.POINTER(Stats)]
         L.caps_sa_gpu_comm_unique_id.argtypes = [p]

@@ -20,6 +20,7 @@ struct caps_sa_gpu_engine {
 namespace {
 
 thread_local std::string g_last_error;
+std::atomic<int> g_cli_byte_mapping{0};  // caps_sa_gpu_set_cli_byte_mapping
 
 template <class F>
 int guarded(F&& body) {
@@ -157,6 +158,7 @@ int construct_host(caps_sa_gpu_engine* engine, const char* text, uint64_t n, Idx
     CAPSB_CUDA(cudaEventRecord(h2d.a, st));
     CAPSB_CUDA(cudaMemcpyAsync(d_text.get(), text, n, cudaMemcpyHostToDevice, st));
     CAPSB_CUDA(cudaEventRecord(h2d.b, st));
+    if (g_cli_byte_mapping.load()) capsb::map_acgt_device(eng, d_text.get(), n);
     capsb::build_sa_lcp<IdxT>(eng, d_text.get(), n, d_sa.get(), d_lcp.get());
     clamp_lcp<IdxT>(eng, d_lcp.get(), n, max_context, n);
     results.finish(d_sa.get(), d_lcp.get(), sa_out, lcp_out, 0, n);
@@ -242,6 +244,7 @@ StagedText stage_text_sharded(Engine& eng, capsb::Comm& comm, const char* text, 
   if (hi > lo) CAPSB_CUDA(cudaMemcpyAsync(out.buf.get() + lo, text + lo, hi - lo, cudaMemcpyHostToDevice, st));
   CAPSB_CUDA(cudaEventRecord(h2d.b, st));
   if (world > 1) comm.all_gather_device(out.buf.get() + rank * piece, out.buf.get(), piece, st);
+  if (g_cli_byte_mapping.load()) capsb::map_acgt_device(eng, out.buf.get(), n);
   CAPSB_CUDA(cudaStreamSynchronize(st));
   out.ms_h2d = h2d.ms();
   return out;
@@ -490,11 +493,14 @@ int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n) {
   });
 }
 
+int caps_sa_gpu_set_cli_byte_mapping(int enabled) { return g_cli_byte_mapping.exchange(enabled ? 1 : 0); }
+
 void* caps_sa_gpu_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+  const cudaError_t err = cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable);
+  if (err != cudaSuccess) {
     cudaGetLastError();
-    g_last_error = "cudaHostAlloc failed";
+    g_last_error = std::string("CUDA error: cudaHostAlloc failed: ") + cudaGetErrorString(err);
     return nullptr;
   }
   return p;

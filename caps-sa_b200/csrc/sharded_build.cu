@@ -112,6 +112,11 @@ void route_backward(Engine& eng, Comm& comm, const Route<IdxT>& r, const T* answ
   launch_map(eng.dev, st, r.m, [=] __device__(uint64_t j) { out(static_cast<uint64_t>(perm[j]), b[j]); });
 }
 
+// A question to the rank that owns a key: the rank (SA position) of `suffix`, whose key it is.
+struct KeyAsk {
+  uint64_t key, suffix;
+};
+
 // ---- ranks sharded by text position ----------------------------------------------------
 // isa_local[pos - lo] = first SA position of suffix pos's group, for suffixes that have been
 // tied; everything else keeps the sentinel.  A lookup that hits the sentinel asks a second
@@ -121,8 +126,8 @@ template <class IdxT>
 struct ShardedRanks {
   using Comp = typename IdxTraits<IdxT>::Comp;
   static constexpr IdxT kUnset = ~IdxT(0);
-  static constexpr bool kPublishesAllTied = true;  // (final suffixes publish their position when the doubling starts)
-  uint64_t resolved_depth = 0;
+  static constexpr bool kPublishesAllTied = false;  // ranks of final suffixes are found by the bucket's owner (rank_of_unpublished)
+  uint64_t resolved_depth = 0;  // set by refine_deep
   Engine& eng;
   Comm& comm;
   SliceMap map;
@@ -131,15 +136,18 @@ struct ShardedRanks {
   const uint64_t* sorted_samples;  // pivot j = sorted_samples[(j + 1) * sample_stride - 1]
   uint64_t sample_stride;
   const uint64_t* bucket_keys;     // this rank's sorted bucket
+  const IdxT* bucket_sa;           // ... and its suffixes (the rank's range of the suffix array, under construction)
+  uint64_t key_symbols;            // symbols the key covers
   uint64_t bucket_count, bucket_offset;
   uint64_t lo;              // first text position of this rank's slice
   uint64_t slice_len = 0;
   DevBuf<IdxT> isa_local;
 
   ShardedRanks(Engine& e, Comm& c, SliceMap m, const PackedText& text, uint64_t mask, const uint64_t* samples,
-               uint64_t stride, const uint64_t* keys, uint64_t count, uint64_t offset)
+               uint64_t stride, const uint64_t* keys, const IdxT* sa, uint64_t key_syms, uint64_t count, uint64_t offset)
       : eng(e), comm(c), map(m), pt(text), key_mask(mask), sorted_samples(samples), sample_stride(stride),
-        bucket_keys(keys), bucket_count(count), bucket_offset(offset), lo(m.begin(static_cast<unsigned>(c.rank))) {
+        bucket_keys(keys), bucket_sa(sa), key_symbols(key_syms), bucket_count(count), bucket_offset(offset),
+        lo(m.begin(static_cast<unsigned>(c.rank))) {
     slice_len = m.end(static_cast<unsigned>(c.rank)) - lo;  // isa_local is allocated by reset()
   }
 
@@ -247,27 +255,25 @@ struct ShardedRanks {
         while (bucket < pivots && samples[static_cast<uint64_t>(bucket + 1) * stride - 1] < key) ++bucket;
         return bucket;
       });
-      DevBuf<uint64_t> asked(rt.recv_total, st);
+      // the question names the suffix as well as its key: a key shared by several (final) suffixes
+      // is resolved inside the owner's bucket by comparing text (rank_of_unpublished)
+      DevBuf<KeyAsk> asked(rt.recv_total, st);
       DevBuf<IdxT> answers(rt.recv_total, st);
-      route_forward<uint64_t>(
+      route_forward<KeyAsk>(
           eng, comm, rt,
-          [=] __device__(uint64_t j) -> uint64_t { return text.window(static_cast<uint64_t>(idx[so[j]]) + h) & mask; },
+          [=] __device__(uint64_t j) -> KeyAsk {
+            const uint64_t ih = static_cast<uint64_t>(idx[so[j]]) + h;
+            return KeyAsk{text.window(ih) & mask, ih};
+          },
           asked.get());
       const uint64_t* keys = bucket_keys;
+      const IdxT* sa = bucket_sa;
       const uint64_t count = bucket_count, offset = bucket_offset;
-      const uint64_t* q = asked.get();
+      const uint64_t ksym = key_symbols, depth = resolved_depth;
+      const KeyAsk* q = asked.get();
       IdxT* a = answers.get();
       launch_map(eng.dev, st, rt.recv_total, [=] __device__(uint64_t j) {
-        const uint64_t want = q[j];
-        uint64_t lo_k = 0, hi_k = count;
-        while (lo_k < hi_k) {
-          const uint64_t mid = (lo_k + hi_k) >> 1;
-          if (keys[mid] < want)
-            lo_k = mid + 1;
-          else
-            hi_k = mid;
-        }
-        a[j] = static_cast<IdxT>(offset + lo_k);
+        a[j] = static_cast<IdxT>(offset + rank_of_unpublished<IdxT>(text, keys, sa, count, q[j].key, q[j].suffix, ksym, depth));
       });
       route_backward<IdxT>(eng, comm, rt, answers.get(), [=] __device__(uint64_t j, IdxT r) { sec[so[j]] = r; });
     }
@@ -602,8 +608,8 @@ void build_sa_lcp_sharded(Engine& eng, Comm& comm, const uint8_t* d_text, uint64
   IdxT* d_lcp = out.lcp.get();
   TiedSet<IdxT> tied;
   {
-    ShardedRanks<IdxT> ranks(eng, comm, map, pt, key_mask_of(key_bits), sorted_samples, kSamplesPerRank, keys,
-                             bucket_count, bucket_offset);
+    ShardedRanks<IdxT> ranks(eng, comm, map, pt, key_mask_of(key_bits), sorted_samples, kSamplesPerRank, keys, d_sa,
+                             key_bits >> log2_bits, bucket_count, bucket_offset);
     refine_tied_groups<IdxT>(eng, ranks, pt, key_bits, keys, d_sa, d_lcp, bucket_count, bucket_offset, n, tied);
   }
   eng.stats.tied_after_key_sort = tied.m;

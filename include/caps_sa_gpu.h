@@ -174,6 +174,13 @@ int caps_sa_gpu_shard_copy(caps_sa_gpu_engine* engine, void* sa_dst, void* lcp_d
  * (reference src/main.cpp:61-70).  `text` is host memory. */
 int caps_sa_gpu_map_acgt(caps_sa_gpu_engine* engine, char* text, uint64_t n);
 
+/* The same mapping fused into the staging of the host-buffer construction calls: when enabled
+ * (process-wide), every caps_sa_gpu_construct_* / _multi_* / _sharded_* call with a host text applies
+ * it to its device copy of the text right after the upload, so a CLI need not push the text
+ * through PCIe three times (up and down for the mapping, up again for the construction).  The
+ * caller's host text is left as it was.  Returns the previous setting. */
+int caps_sa_gpu_set_cli_byte_mapping(int enabled);
+
 /* ---- Pinned host memory ---------------------------------------------------------------------
  * The class shell allocates SA_/LCP_ with these (reference: malloc in the ctor,
  * src/Suffix_Array.cpp:20-21, include/Suffix_Array.hpp:137-142). */

@@ -51,6 +51,9 @@ void caps_oracle_set_threads(int threads);
  * suffix results.  Same codes. */
 int caps_check_sa_lcp_mt(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
                          uint64_t* bad_pos);
+/* ... with the number of ranges Kasai's walk is cut into bounded (highly repetitive texts: one per thread). */
+int caps_check_sa_lcp_mt_pieces(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
+                                uint64_t max_pieces, uint64_t* bad_pos);
 
 /* The same validation for a text that is its first `period` (<= 4096) bytes repeated, with OpenMP
  * loops and the LCP from the closed form for periodic texts (sa_check.c) — for the 1 Gbp

@@ -170,8 +170,19 @@ done:
  * nothing else.  The inverse permutation is stored at the index width of the input (4 bytes for
  * a 32-bit suffix array), so 3.1 G suffixes need 12.4 GB on top of the arrays being checked.
  * Same return codes; bad_pos = the smallest offending SA position of the failing predicate. */
+int caps_check_sa_lcp_mt_pieces(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
+                                uint64_t max_pieces, uint64_t* bad_pos);
+
 int caps_check_sa_lcp_mt(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
                          uint64_t* bad_pos) {
+  return caps_check_sa_lcp_mt_pieces(text, n, sa, lcp, idx_bytes, 0, bad_pos);
+}
+
+/* max_pieces = the number of ranges Kasai's walk is cut into (0: up to 4096).  Every range pays one
+ * comparison from scratch, i.e. up to the longest LCP: on highly repetitive texts (Fibonacci words)
+ * use about one range per thread. */
+int caps_check_sa_lcp_mt_pieces(const char* text, uint64_t n, const void* sa, const void* lcp, int idx_bytes,
+                                uint64_t max_pieces, uint64_t* bad_pos) {
   if ((idx_bytes != 4 && idx_bytes != 8) || !text || !sa || !lcp) return 4;
   if (n == 0) return 0;
   const signed char* t = (const signed char*)text;
@@ -232,6 +243,7 @@ int caps_check_sa_lcp_mt(const char* text, uint64_t n, const void* sa, const voi
   {
     uint64_t pieces = n / 65536 + 1;
     if (pieces > 4096) pieces = 4096;
+    if (max_pieces && pieces > max_pieces) pieces = max_pieces;
 #pragma omp parallel for schedule(dynamic, 1)
     for (uint64_t p = 0; p < pieces; ++p) {
       const uint64_t lo = n / pieces * p, hi = p + 1 == pieces ? n : n / pieces * (p + 1);

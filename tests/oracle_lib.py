@@ -52,6 +52,8 @@ def port():
         lib.caps_oracle_set_threads.restype = None
         lib.caps_check_sa_lcp_mt.argtypes = [p, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp_mt.restype = C.c_int
+        lib.caps_check_sa_lcp_mt_pieces.argtypes = [p, u64, p, p, C.c_int, u64, C.POINTER(u64)]
+        lib.caps_check_sa_lcp_mt_pieces.restype = C.c_int
         lib.caps_check_sa_lcp_periodic.argtypes = [p, u64, u64, p, p, C.c_int, C.POINTER(u64)]
         lib.caps_check_sa_lcp_periodic.restype = C.c_int
         lib.caps_naive_sa_lcp.argtypes = [p, u64, p, p]
@@ -131,7 +133,7 @@ def check_sa_lcp(text, sa: np.ndarray, lcp: np.ndarray):
     return rc, bad.value
 
 
-def check_sa_lcp_mt(text, sa: np.ndarray, lcp: np.ndarray):
+def check_sa_lcp_mt(text, sa: np.ndarray, lcp: np.ndarray, max_pieces: int = 0):
     """check_sa_lcp with OpenMP loops (oracle/sa_check.c: caps_check_sa_lcp_mt): what bench.py applies
     to its full-size results.  No copies are made: pass contiguous arrays."""
     t = _as_text(text)
@@ -140,8 +142,8 @@ def check_sa_lcp_mt(text, sa: np.ndarray, lcp: np.ndarray):
     bad = C.c_uint64(0)
     # all the cores this process may run on, whatever OMP_NUM_THREADS the launcher exported
     port().caps_oracle_set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
-    rc = port().caps_check_sa_lcp_mt(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
-                                     sa.dtype.itemsize, C.byref(bad))
+    rc = port().caps_check_sa_lcp_mt_pieces(t.ctypes.data, len(t), sa.ctypes.data, lcp.ctypes.data,
+                                            sa.dtype.itemsize, max_pieces, C.byref(bad))
     return rc, bad.value
 
 

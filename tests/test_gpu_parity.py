@@ -471,6 +471,7 @@ def test_cli_dump_matches_reference_cli(pkg, synth, tmp_path):
     assert f"Text length: {len(raw)}." in proc.stderr
     assert "Constructed the suffix array. Time taken:" in proc.stderr
     assert "Dumped the suffix array. Time taken:" in proc.stderr
+    assert "Sorted the suffixes by their prefix keys. Time taken:" in proc.stderr  # per-stage lines, in the reference's form
     ref_cli = os.path.join(ROOT, "oracle", "_ref", "caps_sa_ref")
     if os.path.exists(ref_cli):
         out_cpu = tmp_path / "cpu.bin"
@@ -498,6 +499,24 @@ def test_cli_pretty_print(pkg, synth, tmp_path):
     sa, lcp = oracle_lib.port_sa_lcp(mapped, subproblems=16)
     assert np.array_equal(np.array(lines[0].split(), dtype=np.uint64), sa.astype(np.uint64))
     assert np.array_equal(np.array(lines[1].split(), dtype=np.uint64), lcp.astype(np.uint64))
+
+
+def test_cli_byte_mapping_fused_into_staging(pkg, engine, synth):
+    """caps_sa_gpu_set_cli_byte_mapping: the CLI's byte mapping (reference src/main.cpp:61-70) applied to
+    the device copy of the text inside the construction call == constructing the mapped text."""
+    raw = synth.ecoli_like_fasta(seed=3, bases=300_000)
+    want_sa, want_lcp, _ = gpu_sa_lcp(pkg, engine, synth.map_acgt(raw))
+    before = pkg.lib().caps_sa_gpu_set_cli_byte_mapping(1)
+    try:
+        keep = raw.copy()
+        sa, lcp, _ = gpu_sa_lcp(pkg, engine, raw)
+        many = pkg.SuffixArray(raw, devices=[0, 0, 0])
+        many.construct()
+    finally:
+        pkg.lib().caps_sa_gpu_set_cli_byte_mapping(before)
+    assert np.array_equal(raw, keep), "the caller's text must be left as it was"
+    assert np.array_equal(sa, want_sa) and np.array_equal(lcp, want_lcp)
+    assert np.array_equal(many.SA(), want_sa) and np.array_equal(many.LCP(), want_lcp)
 
 
 def test_map_acgt_kernel(engine, synth):

@@ -61,8 +61,10 @@ def main():
             rc, bad = oracle_lib.check_sa_lcp_periodic(text, args.unit, sa, lcp)
             line["checker"] = "caps_check_sa_lcp_periodic (closed-form LCP, OpenMP)"
         else:
-            rc, bad = oracle_lib.check_sa_lcp(text, sa, lcp)
-            line["checker"] = "caps_check_sa_lcp (ISA order + Kasai)"
+            # Kasai's walk in one range per thread: every range pays one comparison from scratch, and the
+            # common prefixes of a Fibonacci word run to hundreds of millions of symbols
+            rc, bad = oracle_lib.check_sa_lcp_mt(text, sa, lcp, max_pieces=len(os.sched_getaffinity(0)))
+            line["checker"] = "caps_check_sa_lcp_mt (ISA order + Kasai, OpenMP, one range per thread)"
         line["check_s"] = round(time.time() - t0, 1)
         line["check_code"] = rc
         line["check_bad_position"] = bad
