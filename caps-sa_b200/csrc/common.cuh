@@ -5,7 +5,7 @@
 //     (bench.py reports the count as "gpu_launches");
 //   * every CUDA call goes through CAPSB_CUDA, which throws capsb::Error; the C-ABI
 //     layer (capi.cu) turns that into a non-zero return code + caps_sa_gpu_last_error();
-//   * device scratch comes from the stream-ordered pool (cudaMallocAsync) through DevBuf;
+//   * device scratch comes from the engine's slab arena (Arena, below) through DevBuf;
 //   * streaming kernels use a fixed grid (a multiple of the SM count) and walk
 //     contiguous chunks, so per-block partials stay small and scans are 3 short kernels.
 #pragma once

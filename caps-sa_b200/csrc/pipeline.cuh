@@ -968,12 +968,9 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     });
     trace_point(eng, "  round: classified + small groups counted");
     constexpr size_t kSortSmem = (sizeof(CompT) + sizeof(IdxT)) * kMidGroup;
-    static bool configured[64] = {};
-    if (!configured[dev.device & 63]) {
-      CAPSB_CUDA(cudaFuncSetAttribute(group_sort_kernel<CompT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(kSortSmem)));
-      configured[dev.device & 63] = true;
-    }
+    // (every launch: the attribute is per context, and host threads of other ranks may be here too)
+    CAPSB_CUDA(cudaFuncSetAttribute(group_sort_kernel<CompT, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(kSortSmem)));
     const uint64_t want = mid_capacity < static_cast<uint64_t>(dev.sm_count) * 8 ? mid_capacity
                                                                                    : static_cast<uint64_t>(dev.sm_count) * 8;
     CAPSB_LAUNCH((group_sort_kernel<CompT, IdxT>), static_cast<unsigned>(want), kGroupSortThreads, kSortSmem, st,

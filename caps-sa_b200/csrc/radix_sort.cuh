@@ -442,13 +442,10 @@ template <class KeyT, class ValT, class Src, int kThreads, int kItems, int kMinB
 inline void launch_scatter_variant(cudaStream_t stream, RadixScratch& rs, const Chunking& ck, Src src, uint64_t n,
                                    unsigned shift, KeyT* keys_out, ValT* vals_out) {
   constexpr size_t kSmem = sizeof(ScatterSmem<KeyT, ValT, kThreads, kItems, kPrefetch>);
-  static bool configured[64] = {};  // per template instantiation and device (the attribute is per context)
-  const int slot = rs.device & 63;
-  if (!configured[slot] || rs.device >= 64) {
-    CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks, kPrefetch>,
-                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
-    configured[slot] = true;
-  }
+  // every launch: the attribute belongs to the current context (one per device), several host threads
+  // may drive several devices at once, and the call costs a few hundred nanoseconds
+  CAPSB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks, kPrefetch>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem)));
   CAPSB_LAUNCH((radix_scatter_kernel<KeyT, ValT, Src, kThreads, kItems, kMinBlocks, kPrefetch>), ck.blocks, kThreads,
                kSmem, stream, src, n, ck.chunk, shift, rs.hist.get(), rs.digit_total.get(), keys_out, vals_out);
 }

@@ -1,22 +1,27 @@
 // Sharded (multi-GPU) suffix-array + LCP construction: the samplesort shape of the reference
-// (src/Suffix_Array.cpp:466-494) with one rank per GPU.
+// (src/Suffix_Array.cpp:466-494) with one rank per GPU.  Default order of stages (partition first):
 //
 //   text              replicated: every rank stages and packs the whole text in its HBM
-//   sort_subarrays    (:161-184)  rank r key-sorts the suffixes that start in its slice of the
-//                                 text (last slice takes the remainder, as :172)
-//   select_pivots     (:197-222)  regular samples of every sorted slice, all-gathered; every
-//                                 rank sorts the same sample set and picks the same G-1 pivots
-//   locate_pivots     (:225-249)  warp-cooperative upper-bound search of each pivot in the
-//                                 sorted slice -> send counts; all-gather -> the G x G matrix P
-//   partition/collate (:300-368)  variable all-to-all of (key, suffix) runs over NVLink
-//   merge_sub_subarrays (:371-428) merge-path tree over the G received runs (merge_path.cuh)
-//   ties                          prefix doubling on ranks sharded by text position: one
-//                                 request/response exchange and one update exchange per round
+//   select_pivots     (:197-222)  1024 sampled keys of the rank's slice of the text (last slice takes the
+//                                 remainder, as :172), all-gathered; every rank sorts the same sample set
+//                                 and picks the same G-1 key pivots
+//   locate_pivots + partition (:225-368)  one counting pass over the slice with the bucket (binary search
+//                                 among the pivots) as digit -> the slice's suffixes grouped by bucket, in
+//                                 text order; send counts all-gathered -> the G x G matrix P
+//   collate           (:335-364)  all-to-all of suffix INDICES over NVLink (keys are re-derived from the
+//                                 replicated text); CAPSB_SHARD_P2P=1: the partition kernel stores straight
+//                                 into the owners' buckets instead (partition.cuh; measured slower at two GPUs)
+//   sort_subarrays / merge_sub_subarrays (:161-184, :371-428)  the rank key-sorts its bucket (packed-record
+//                                 MSD sort, msd_sort.cuh)
+//   ties                          pair chains and text rounds are local to the rank; prefix doubling on ranks
+//                                 sharded by text position: per round one request/response exchange and one
+//                                 update exchange; ranks of final suffixes are found by the owner of their key
 //   LCP               (:61-68,:78,:431-447) neighbours with different keys: from the keys (the
-//                                 predecessor of a bucket's first suffix comes from the
-//                                 previous rank = the reference's boundary patch); tied
-//                                 neighbours travel to the rank that owns their text position,
-//                                 where the permuted-LCP chains are contiguous, and back.
+//                                 predecessor of a bucket's first suffix comes from the previous rank = the
+//                                 reference's boundary patch); tied neighbours travel to the rank that owns
+//                                 their text position, where the permuted-LCP chains are contiguous, and back.
+// CAPSB_SHARD_MODE=merge keeps the reference's own order (sort the slices, locate the pivots in the sorted
+// slices, exchange sorted (key, suffix) runs, merge-path tree over the received runs).
 // Pivots are keys, so suffixes with equal keys land on one rank and tie groups never span
 // ranks; rank r ends up owning the contiguous range [offset, offset + count) of SA and LCP.
 #include "comm.cuh"

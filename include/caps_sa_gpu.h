@@ -123,12 +123,14 @@ int caps_sa_gpu_construct_device_u64(caps_sa_gpu_engine* engine, const void* d_t
 
 /* ---- Sharded construction: several GPUs, one rank each -------------------------------------
  * The samplesort shape of the reference (src/Suffix_Array.cpp:466-494) across ranks: the text
- * is replicated, rank r key-sorts the suffixes of its slice of the text (sort_subarrays,
- * :161-184), pivots are agreed from all-gathered samples (select_pivots, :197-222), located in
- * every sorted slice (locate_pivots, :225-249), (key, suffix) runs move to the rank that owns
- * their bucket in one all-to-all (partition_sub_subarrays, :300-368), each rank merges its
- * runs (merge_sub_subarrays, :371-428), and the LCP at bucket boundaries comes from the
- * neighbouring rank (compute_partition_boundary_lcp, :431-447).  Rank r ends up owning the
+ * is replicated; pivots are agreed from all-gathered key samples of every rank's slice of the text
+ * (select_pivots, :197-222); one counting pass groups the slice's suffixes by bucket
+ * (locate_pivots + partition_sub_subarrays, :225-368); suffix indices move to the rank that owns
+ * their bucket in one all-to-all (the collate step, :335-364); each rank key-sorts its bucket and
+ * resolves its ties (sort_subarrays / merge_sub_subarrays, :161-184, :371-428); the LCP at bucket
+ * boundaries comes from the neighbouring rank (compute_partition_boundary_lcp, :431-447).
+ * CAPSB_SHARD_MODE=merge selects the reference's own order of stages instead (sort the slices, locate
+ * the pivots in them, exchange sorted (key, suffix) runs, merge).  Rank r ends up owning the
  * contiguous range [shard_offset, shard_offset + shard_count) of SA and LCP.
  *
  * (1) One process, one host thread per rank (what Suffix_Array<idx_t>::construct() binds when
