@@ -503,15 +503,28 @@ __device__ __forceinline__ void msd_local_pass(Smem& sm, uint64_t (&rec)[kN], un
   unsigned rk[(kN + 1) / 2];  // two 16-bit ranks per register; the digit is recomputed from the record
   const bool has0 = tid < count;
   const bool aggregate = msd_probe(has0 ? (static_cast<unsigned>(rec[0] >> shift) & mask) : bins, has0);
+  if (!aggregate) {
 #pragma unroll
-  for (int t = 0; t < kN; ++t) {
-    const unsigned e = static_cast<unsigned>(t) * kT + tid;
-    const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
-    const unsigned r = msd_count(sm.cnt, msd_pad(d), d != bins, aggregate, lane, lt);
-    if (t & 1)
-      rk[t >> 1] |= r << 16;
-    else
-      rk[t >> 1] = r;
+    for (int t = 0; t < kN; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kT + tid;
+      unsigned r = 0;
+      if (e < count) r = atomicAdd(&sm.cnt[msd_pad(static_cast<unsigned>(rec[t] >> shift) & mask)], 1u);
+      if (t & 1)
+        rk[t >> 1] |= r << 16;
+      else
+        rk[t >> 1] = r;
+    }
+  } else {
+#pragma unroll
+    for (int t = 0; t < kN; ++t) {
+      const unsigned e = static_cast<unsigned>(t) * kT + tid;
+      const unsigned d = e < count ? (static_cast<unsigned>(rec[t] >> shift) & mask) : bins;
+      const unsigned r = msd_count(sm.cnt, msd_pad(d), d != bins, true, lane, lt);
+      if (t & 1)
+        rk[t >> 1] |= r << 16;
+      else
+        rk[t >> 1] = r;
+    }
   }
   __syncthreads();
   {  // eight consecutive counters per thread
@@ -556,12 +569,13 @@ __device__ __forceinline__ void msd_local_pass(Smem& sm, uint64_t (&rec)[kN], un
 template <int kN, int kT, class Smem>
 __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict__ recs,
                                                  uint32_t* __restrict__ sa_out, uint32_t q, uint32_t beg, uint32_t count,
-                                                 unsigned rem_bits, unsigned key_shift) {
+                                                 unsigned rem_bits, unsigned key_shift, unsigned extra_bits) {
   const unsigned tid = threadIdx.x;
-  // The first counting pass takes the top hb of the remaining bits: about one counter per two
-  // records (the scan of the counters is per-bucket overhead), at least rem_bits - 12 so that
-  // one more pass can finish a large group, at most 12.
-  unsigned hb = count > 4 ? 31u - static_cast<unsigned>(__clz(count - 1u)) : 1u;  // smallest hb with 2^(hb+1) >= count
+  // The first counting pass takes the top hb of the remaining bits: about one counter per record
+  // (extra_bits = 1; per two records with 0 — the scan of the counters is per-bucket overhead, the
+  // comparison loop of the groups grows with the records per counter), at least rem_bits - 12 so
+  // that one more pass can finish a large group, at most 12.
+  unsigned hb = (count > 4 ? 31u - static_cast<unsigned>(__clz(count - 1u)) : 1u) + extra_bits;  // 2^(hb+1-extra) >= count
   if (hb > static_cast<unsigned>(kMsdLocalBits)) hb = kMsdLocalBits;
   if (hb + kMsdLocalBits < rem_bits) hb = rem_bits - kMsdLocalBits;
   if (hb > rem_bits) hb = rem_bits;
@@ -597,9 +611,15 @@ __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict_
         if (g1 - g0 <= kMsdSmallGroup) {
           const unsigned mine = static_cast<unsigned>(r >> 32);
           unsigned rank = 0;
-          for (unsigned u = g0; u < g1; ++u) {
+          if (g1 - g0 == 2) {  // (most records sit in groups of one or two: no loop for them)
+            const unsigned u = s == g0 ? g0 + 1 : g0;
             const unsigned other = static_cast<unsigned>(sm.stage[u] >> 32);
-            rank += (other < mine || (other == mine && u < s)) ? 1u : 0u;
+            rank = (other < mine || (other == mine && u < s)) ? 1u : 0u;
+          } else if (g1 - g0 > 2) {
+            for (unsigned u = g0; u < g1; ++u) {
+              const unsigned other = static_cast<unsigned>(sm.stage[u] >> 32);
+              rank += (other < mine || (other == mine && u < s)) ? 1u : 0u;
+            }
           }
           recs[beg + g0 + rank] = (prefix | (static_cast<uint64_t>(mine) & rem_mask)) << key_shift;
           sa_out[beg + g0 + rank] = static_cast<uint32_t>(r);
@@ -651,7 +671,8 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
                                                                  const uint32_t* __restrict__ child_start,
                                                                  const uint32_t* __restrict__ bucket_list,
                                                                  uint32_t q_begin, uint32_t q_end, unsigned key_bits,
-                                                                 unsigned prefix_bits, uint32_t* __restrict__ sa_out,
+                                                                 unsigned prefix_bits, unsigned extra_bits,
+                                                                 uint32_t* __restrict__ sa_out,
                                                                  uint32_t* __restrict__ large_list,
                                                                  uint32_t* __restrict__ large_count) {
   extern __shared__ __align__(16) unsigned char msd_smem_raw[];
@@ -674,9 +695,9 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
       continue;
     }
     if (count <= static_cast<uint32_t>(kHalf * kT))
-      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
+      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits);
     else
-      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift);
+      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits);
   }
 }
 

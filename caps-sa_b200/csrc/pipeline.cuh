@@ -242,6 +242,9 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
   uint32_t* counts = ms.large_count.get();  // [0] buckets too large for the first kernel, [1] for the second
   CAPSB_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(uint32_t), st));
   uint32_t* huge_list = ms.large_list.get() + ms.large_capacity;
+  // CAPSB_MSD_LOCAL_EXTRA=0: one counter per two records in the first local counting pass (default 1: one per record)
+  unsigned extra_bits = 1;
+  if (const char* env = std::getenv("CAPSB_MSD_LOCAL_EXTRA")) extra_bits = static_cast<unsigned>(std::atoi(env)) & 3u;
   {
     using Small = MsdLocalSmem<kMsdLocalCap>;
     msd_allow_smem(msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>, sizeof(Small));
@@ -249,7 +252,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     MsdTimed timed(eng.msd_timers.local, st, records * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
     CAPSB_LAUNCH((msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>), grid, kMsdThreads, sizeof(Small), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(nullptr), q_begin, q_end, ms.key_bits, ms.a + ms.b,
-                 sa_out, ms.large_list.get(), counts);
+                 extra_bits, sa_out, ms.large_list.get(), counts);
   }
   uint32_t nlarge = 0;
   read_back(st, &nlarge, counts, sizeof(uint32_t));
@@ -260,7 +263,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     const uint32_t grid = std::min<uint32_t>(nlarge, static_cast<uint32_t>(dev.sm_count));
     CAPSB_LAUNCH((msd_local_kernel<kMsdBigThreads, 1>), grid, kMsdBigThreads, sizeof(Big), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(ms.large_list.get()), 0u, nlarge, ms.key_bits,
-                 ms.a + ms.b, sa_out, huge_list, counts + 1);
+                 ms.a + ms.b, extra_bits, sa_out, huge_list, counts + 1);
   }
   uint32_t nhuge = 0;
   read_back(st, &nhuge, counts + 1, sizeof(uint32_t));
