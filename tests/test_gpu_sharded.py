@@ -67,12 +67,8 @@ def test_sharded_matches_oracle(pkg, synth, case, ranks):
 
 
 # The fused partition pass (CAPSB_SHARD_P2P=1: suffix indices stored straight into the owners'
-# buckets, csrc/partition.cuh) is experimental and has not run on a GPU yet; its tests are opt-in
-# (CAPSB_TEST_P2P=1) until it has.
-p2p_opt_in = pytest.mark.skipif(os.environ.get("CAPSB_TEST_P2P") != "1", reason="experimental path: set CAPSB_TEST_P2P=1")
-
-
-@p2p_opt_in
+# buckets, csrc/partition.cuh).  Correct on one and two GPUs, thread and NCCL/CUDA-IPC transports
+# (profiles/r02 s08), but slower than the partition pass + ncclSend/Recv it would replace: off by default.
 @pytest.mark.parametrize("ranks", [1, 2, 3, 8])
 @pytest.mark.parametrize("case", ["acgt_1M", "genome_like_2M", "bytes256_300k", "fibonacci_200k", "allA_50k"])
 def test_sharded_p2p_partition_matches_oracle(pkg, synth, case, ranks, monkeypatch):
@@ -167,7 +163,6 @@ def test_one_process_per_gpu_nccl(pkg):
     assert proc.returncode == 0 and "SHARDED_CHECK PASSED" in proc.stdout, proc.stdout[-3000:] + proc.stderr[-3000:]
 
 
-@p2p_opt_in
 def test_one_process_per_gpu_nccl_p2p_partition(pkg):
     """The fused partition pass under torchrun: the bucket buffers cross the process boundary as
     CUDA IPC handles (needs at least two GPUs)."""
