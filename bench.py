@@ -72,13 +72,18 @@ KERNEL_CLASSES = {
     "scatter": ("radix_scatter_kernel", "(u64 key, u32 suffix) pairs read once and written once: 24 B per pair"),
     "msd_scatter_a": ("msd_scatter_kernel, level A", "text window read (~1 B) + one 8-byte record written per suffix"),
     "msd_scatter_b": ("msd_scatter_kernel, level B", "one 8-byte record read and written per suffix: 16 B"),
-    "msd_local": ("msd_local_kernel", "8-byte record read, 8-byte key + 4-byte suffix written: 20 B per suffix"),
+    "msd_local": ("msd_local_kernel (both instantiations: 512 threads, and 1024 threads for the buckets of 6145..12288 records)",
+                  "8-byte record read, 8-byte key + 4-byte suffix written: 20 B per suffix"),
     "msd_hist": ("msd_hist_kernel", "text window (level A) or one 8-byte record (level B) read per suffix"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch over the algorithmic bytes of the launch, from the
 # committed `ncu --set full` captures (profiles/): filled in per kernel class as they are captured
+_S14 = "profiles/r02/ncu_full_msd_kernels_s14.csv"  # one construction of the 3.1 Gbp workload, 3.1e9 records per level
 NCU_TRAFFIC = {
     "scatter": (NCU_TRAFFIC_RATIO, "profiles/r01/scatter_ncu_full_v4.csv"),
+    "msd_scatter_a": ((0.798767e9 + 29.127431e9) / (9.0 * 3.1e9), _S14),
+    "msd_scatter_b": ((25.027414e9 + 24.795954e9) / (16.0 * 3.1e9), _S14),
+    "msd_local": ((23.623950e9 + 35.203882e9 + 1.299756e9 + 1.885538e9) / (20.0 * 3.1e9), _S14),
 }
 
 

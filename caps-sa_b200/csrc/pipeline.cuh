@@ -261,6 +261,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     using Big = MsdLocalSmem<kMsdBigThreads * kMsdItems>;
     msd_allow_smem(msd_local_kernel<kMsdBigThreads, 1>, sizeof(Big));
     const uint32_t grid = std::min<uint32_t>(nlarge, static_cast<uint32_t>(dev.sm_count));
+    MsdTimed timed(eng.msd_timers.local, st, 0);  // (its records are counted with the first launch)
     CAPSB_LAUNCH((msd_local_kernel<kMsdBigThreads, 1>), grid, kMsdBigThreads, sizeof(Big), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(ms.large_list.get()), 0u, nlarge, ms.key_bits,
                  ms.a + ms.b, extra_bits, sa_out, huge_list, counts + 1);
@@ -1269,15 +1270,19 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
   // what is left needs the depth to double (refine_deep).
   const uint64_t text_step = 63u >> log2_bits;  // symbols a text round advances
   bool try_pairs = true;
+  // The first text round runs before any pair-chain step: it separates most pairs anyway (and settles
+  // their LCPs), so chaining them first costs more passes over the full list than it saves the round
+  // (3.1 Gbp: 182.3 -> 179.1 ms, profiles/r02 s14).  CAPSB_PAIRS_FIRST=1 restores the other order.
+  static const bool pairs_first = std::getenv("CAPSB_PAIRS_FIRST") && std::getenv("CAPSB_PAIRS_FIRST")[0] == '1';
   for (unsigned iter = 0; total_active > 0; ++iter) {
     // groups of two are finished directly (order and LCP).  The step is a few passes over the
     // list, so it stops once it no longer thins the list out.
-    if (try_pairs) {
+    if (try_pairs && (pairs_first || iter > 0)) {
       if (trace) round_start = std::chrono::steady_clock::now();
       const uint64_t before = total_active;
       resolve_pairs<IdxT>(eng, ranks, act, d_sa, d_lcp, pos_base, h, false);
       total_active = ranks.global_sum(act.m);
-      try_pairs = iter < 2 || (before - total_active) * 16 >= before;
+      try_pairs = iter < (pairs_first ? 2u : 3u) || (before - total_active) * 16 >= before;
       lap("pair chains", before);
       if (total_active == 0) break;
     }
