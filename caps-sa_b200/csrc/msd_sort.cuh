@@ -46,7 +46,7 @@ constexpr int kMsdLocalBits = 12;                  // digit width of the countin
 constexpr int kMsdLocalBins = 1 << kMsdLocalBits;
 constexpr int kMsdLocalCap = kMsdTile;             // largest bucket the two-CTAs-per-SM local sort takes
 constexpr int kMsdBigThreads = 1024;               // second instantiation: one CTA per SM, twice the bucket
-constexpr unsigned kMsdSmallGroup = 32;            // groups up to this size are ordered by comparison
+constexpr unsigned kMsdSmallGroup = 32;            // groups up to AT LEAST this size are ordered by comparison (the limit is a kernel argument)
 static_assert(kMsdTile <= 8192 && kMsdThreads % 32 == 0, "ranks are packed in 13 / 16 bits");
 
 // A piece = the part of one parent bucket that one CTA partitions: records [begin, end).
@@ -569,7 +569,8 @@ __device__ __forceinline__ void msd_local_pass(Smem& sm, uint64_t (&rec)[kN], un
 template <int kN, int kT, class Smem>
 __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict__ recs,
                                                  uint32_t* __restrict__ sa_out, uint32_t q, uint32_t beg, uint32_t count,
-                                                 unsigned rem_bits, unsigned key_shift, unsigned extra_bits) {
+                                                 unsigned rem_bits, unsigned key_shift, unsigned extra_bits,
+                                                 unsigned small_group) {
   const unsigned tid = threadIdx.x;
   // The first counting pass takes the top hb of the remaining bits: about one counter per record
   // (extra_bits = 1; per two records with 0 — the scan of the counters is per-bucket overhead, the
@@ -608,7 +609,7 @@ __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict_
         const uint64_t r = sm.stage[s];
         const unsigned d = static_cast<unsigned>(r >> (32u + lb)) & hmask;
         const unsigned g0 = sm.start[msd_pad(d)], g1 = sm.start[msd_pad(d + 1)];
-        if (g1 - g0 <= kMsdSmallGroup) {
+        if (g1 - g0 <= small_group) {
           const unsigned mine = static_cast<unsigned>(r >> 32);
           unsigned rank = 0;
           if (g1 - g0 == 2) {  // (most records sit in groups of one or two: no loop for them)
@@ -672,7 +673,7 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
                                                                  const uint32_t* __restrict__ bucket_list,
                                                                  uint32_t q_begin, uint32_t q_end, unsigned key_bits,
                                                                  unsigned prefix_bits, unsigned extra_bits,
-                                                                 uint32_t* __restrict__ sa_out,
+                                                                 unsigned small_group, uint32_t* __restrict__ sa_out,
                                                                  uint32_t* __restrict__ large_list,
                                                                  uint32_t* __restrict__ large_count) {
   extern __shared__ __align__(16) unsigned char msd_smem_raw[];
@@ -695,9 +696,9 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
       continue;
     }
     if (count <= static_cast<uint32_t>(kHalf * kT))
-      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits);
+      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group);
     else
-      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits);
+      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group);
   }
 }
 

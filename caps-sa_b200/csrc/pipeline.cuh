@@ -245,6 +245,19 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
   // CAPSB_MSD_LOCAL_EXTRA=0: one counter per two records in the first local counting pass (default 1: one per record)
   unsigned extra_bits = 1;
   if (const char* env = std::getenv("CAPSB_MSD_LOCAL_EXTRA")) extra_bits = static_cast<unsigned>(std::atoi(env)) & 3u;
+  // Groups of records that share the first pass's digit are ordered by comparison up to this size, by a
+  // second counting pass above it.  A pass costs a bucket a fixed few microseconds (barriers, the scan
+  // of the counters) whatever the group's size, the comparison loop size^2 shared-memory reads spread
+  // over the CTA: the pass only pays for groups of hundreds.  3.1 Gbp, local sort per construction:
+  // 40.2 ms with 32 / 32, 36.9 with 32 / 256, 36.0 with 128 / 256, 36.9 with 256 / 512 (profiles/r02 s17).
+  // (CAPSB_MSD_SMALL_GROUP[_BIG]: tuning.)
+  auto group_limit = [](const char* name, unsigned dflt) {
+    const char* env = std::getenv(name);
+    const long v = env ? std::atol(env) : static_cast<long>(dflt);
+    return static_cast<unsigned>(v < static_cast<long>(kMsdSmallGroup) ? kMsdSmallGroup : v > 2048 ? 2048 : v);
+  };
+  const unsigned small_group = group_limit("CAPSB_MSD_SMALL_GROUP", 128);
+  const unsigned small_group_big = group_limit("CAPSB_MSD_SMALL_GROUP_BIG", 256);
   {
     using Small = MsdLocalSmem<kMsdLocalCap>;
     msd_allow_smem(msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>, sizeof(Small));
@@ -252,7 +265,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     MsdTimed timed(eng.msd_timers.local, st, records * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
     CAPSB_LAUNCH((msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>), grid, kMsdThreads, sizeof(Small), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(nullptr), q_begin, q_end, ms.key_bits, ms.a + ms.b,
-                 extra_bits, sa_out, ms.large_list.get(), counts);
+                 extra_bits, small_group, sa_out, ms.large_list.get(), counts);
   }
   uint32_t nlarge = 0;
   read_back(st, &nlarge, counts, sizeof(uint32_t));
@@ -264,7 +277,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     MsdTimed timed(eng.msd_timers.local, st, 0);  // (its records are counted with the first launch)
     CAPSB_LAUNCH((msd_local_kernel<kMsdBigThreads, 1>), grid, kMsdBigThreads, sizeof(Big), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(ms.large_list.get()), 0u, nlarge, ms.key_bits,
-                 ms.a + ms.b, extra_bits, sa_out, huge_list, counts + 1);
+                 ms.a + ms.b, extra_bits, small_group_big, sa_out, huge_list, counts + 1);
   }
   uint32_t nhuge = 0;
   read_back(st, &nhuge, counts + 1, sizeof(uint32_t));
@@ -751,11 +764,124 @@ void resolve_pairs(Engine& eng, Ranks& ranks, ActiveList<IdxT>& act, IdxT* d_sa,
 }
 
 // Groups of kSmallGroup < size <= kMidGroup suffixes (the bulk of a repeat family's ties) are
-// sorted by one CTA each, in shared memory (bitonic network on (comp, suffix)): two passes over
-// their elements in HBM instead of the 7-9 radix passes the global sort would spend on them.
+// sorted on chip, by a bitonic network on (comp, suffix) held in REGISTERS: two passes over their
+// elements in HBM instead of the 7-9 radix passes the global sort would spend on them.  The
+// cooperating threads (a warp, or the CTA for the larger groups) hold kE consecutive network
+// positions each, so a compare-exchange step is
+//   * register moves                      when its stride stays inside a thread  (stride < kE),
+//   * one shuffle per 32-bit word         when it stays inside a warp            (stride < 32 kE),
+//   * a trip through shared memory        otherwise (6 of the 78 steps of a 4096-element sort).
+// (The first version kept the whole group in shared memory and paid four loads and up to four
+// stores per exchange plus a barrier per step: 17.5 ms per construction at 3.1 Gbp, profiles/r02.)
 constexpr unsigned kMidGroup = 4096;
 constexpr int kGroupSortThreads = 256;
+constexpr unsigned kWarpGroup = 256;  // up to here a warp sorts the group, above it a CTA does
 
+template <class T>
+__device__ __forceinline__ T shfl_xor_words(T x, unsigned lane_mask) {
+  static_assert(sizeof(T) % 4 == 0, "shuffled 32 bits at a time");
+  constexpr int kWords = sizeof(T) / 4;
+  uint32_t w[kWords];
+  memcpy(w, &x, sizeof(T));
+#pragma unroll
+  for (int i = 0; i < kWords; ++i) w[i] = __shfl_xor_sync(0xffffffffu, w[i], lane_mask);
+  T r;
+  memcpy(&r, w, sizeof(T));
+  return r;
+}
+
+// (comp, suffix) pairs are distinct except for the padding, whose copies are interchangeable.
+template <class CompT, class IdxT>
+__device__ __forceinline__ void compare_exchange(CompT& a, IdxT& va, CompT& b, IdxT& vb, bool up) {
+  const bool greater = a > b || (a == b && va > vb);
+  if (greater == up) {
+    const CompT ta = a;
+    a = b, b = ta;
+    const IdxT tv = va;
+    va = vb, vb = tv;
+  }
+}
+
+template <class CompT, class IdxT>
+__device__ __forceinline__ void keep_one(CompT& k, IdxT& v, CompT other_k, IdxT other_v, bool keep_min) {
+  const bool mine_greater = k > other_k || (k == other_k && v > other_v);
+  if (mine_greater == keep_min) k = other_k, v = other_v;
+}
+
+// Sorts kE * kT pairs ascending: thread t of the kT cooperating ones (a warp: kT == 32, or the
+// whole CTA) passes any kE of them and leaves with the pairs of rank t * kE .. t * kE + kE - 1.
+// sk / sv: kE * kT staging elements in shared memory, used only when kT > 32.
+template <class CompT, class IdxT, int kE, int kT>
+__device__ __forceinline__ void bitonic_sort_blocked(CompT (&k)[kE], IdxT (&v)[kE], unsigned t, CompT* sk, IdxT* sv) {
+  constexpr unsigned kTotal = static_cast<unsigned>(kE) * kT;
+  const unsigned base = t * kE;  // network position of k[0]
+  // merges that stay inside a thread
+#pragma unroll
+  for (unsigned span = 2; span <= static_cast<unsigned>(kE); span <<= 1) {
+#pragma unroll
+    for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+      for (unsigned i = 0; i < static_cast<unsigned>(kE); ++i)
+        if ((i & stride) == 0) compare_exchange(k[i], v[i], k[i | stride], v[i | stride], ((base + i) & span) == 0);
+    }
+  }
+#pragma unroll 1
+  for (unsigned span = 2 * kE; span <= kTotal; span <<= 1) {
+    const bool up = (base & span) == 0;  // the same for all kE positions: span > kE
+    unsigned stride = span >> 1;
+    if constexpr (kT > 32) {
+#pragma unroll 1
+      for (; stride >= 32u * kE; stride >>= 1) {  // the partner thread sits in another warp
+        const unsigned partner = t ^ (stride / kE);
+        const bool keep_min = (t < partner) == up;
+        __syncthreads();  // the previous trip's readers are done
+#pragma unroll
+        for (int i = 0; i < kE; ++i) sk[i * kT + t] = k[i], sv[i * kT + t] = v[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < kE; ++i) keep_one(k[i], v[i], sk[i * kT + partner], sv[i * kT + partner], keep_min);
+      }
+    }
+#pragma unroll 1
+    for (; stride >= static_cast<unsigned>(kE); stride >>= 1) {  // the partner is a lane of this warp
+      const unsigned lane_mask = stride / kE;
+      const bool keep_min = ((t & lane_mask) == 0) == up;
+#pragma unroll
+      for (int i = 0; i < kE; ++i) keep_one(k[i], v[i], shfl_xor_words(k[i], lane_mask), shfl_xor_words(v[i], lane_mask), keep_min);
+    }
+#pragma unroll
+    for (unsigned s = kE >> 1; s > 0; s >>= 1) {
+#pragma unroll
+      for (unsigned i = 0; i < static_cast<unsigned>(kE); ++i)
+        if ((i & s) == 0) compare_exchange(k[i], v[i], k[i | s], v[i | s], up);
+    }
+  }
+}
+
+// One group of `size` <= kE * kT pairs starting at `first`: loaded (coalesced; which network
+// position a pair starts from does not matter), padded with pairs that sort last, sorted, stored.
+template <class CompT, class IdxT, int kE, int kT>
+__device__ __forceinline__ void sort_one_group(uint64_t first, unsigned size, unsigned t, const CompT* __restrict__ comp_in,
+                                               const IdxT* __restrict__ idx_in, CompT* __restrict__ comp_out,
+                                               IdxT* __restrict__ idx_out, CompT* sk, IdxT* sv) {
+  CompT k[kE];
+  IdxT v[kE];
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    const unsigned e = i * kT + t;
+    // padding sorts last: largest comp and a suffix index no suffix has
+    k[i] = e < size ? comp_in[first + e] : ~CompT(0);
+    v[i] = e < size ? idx_in[first + e] : ~IdxT(0);
+  }
+  bitonic_sort_blocked<CompT, IdxT, kE, kT>(k, v, t, sk, sv);
+#pragma unroll
+  for (int i = 0; i < kE; ++i) {
+    const unsigned e = t * kE + i;
+    if (e < size) comp_out[first + e] = k[i], idx_out[first + e] = v[i];
+  }
+}
+
+// kWarpGroup < size <= kMidGroup: one CTA per group at a time.
 template <class CompT, class IdxT>
 __global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const IdxT* __restrict__ group_first,
                                                                        const IdxT* __restrict__ group_size,
@@ -765,67 +891,29 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_kernel(const Idx
                                                                        CompT* __restrict__ comp_out,
                                                                        IdxT* __restrict__ idx_out) {
   extern __shared__ __align__(16) unsigned char group_sort_smem[];
-  CompT* k = reinterpret_cast<CompT*>(group_sort_smem);
-  IdxT* v = reinterpret_cast<IdxT*>(group_sort_smem + sizeof(CompT) * kMidGroup);
+  CompT* sk = reinterpret_cast<CompT*>(group_sort_smem);
+  IdxT* sv = reinterpret_cast<IdxT*>(group_sort_smem + sizeof(CompT) * kMidGroup);
+  constexpr int kT = kGroupSortThreads;
+  static_assert(kMidGroup == 16u * kT, "the largest group fills sixteen registers per thread");
   const unsigned long long groups = *group_count;
   for (unsigned long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
     const uint64_t first = group_first[grp];
     const unsigned size = static_cast<unsigned>(group_size[grp]);
-    unsigned padded = 64;
-    while (padded < size) padded <<= 1;
-    for (unsigned e = threadIdx.x; e < padded; e += kGroupSortThreads) {
-      // padding sorts last: largest key and a suffix index no suffix has
-      k[e] = e < size ? comp_in[first + e] : ~CompT(0);
-      v[e] = e < size ? idx_in[first + e] : ~IdxT(0);
-    }
-    __syncthreads();
-    // Every warp owns a contiguous eighth of the padded group: compare-exchange steps whose
-    // stride stays inside it (all but the last few of each merge) need only a warp barrier.
-    const unsigned warp_pairs = padded >> 4;  // pairs per warp's range (padded / 8 elements)
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    auto exchange = [&](unsigned pr, unsigned span, unsigned stride) {
-      const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
-      const unsigned j = i | stride;
-      const bool up = (i & span) == 0;
-      const CompT a = k[i], b = k[j];
-      const IdxT va = v[i], vb = v[j];
-      const bool greater = a > b || (a == b && va > vb);  // (comp, suffix) pairs are distinct
-      if (greater == up) {
-        k[i] = b, k[j] = a;
-        v[i] = vb, v[j] = va;
-      }
-    };
-    bool block_wide = false;  // was the previous step synchronised across the block?
-    for (unsigned span = 2; span <= padded; span <<= 1) {
-      for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
-        if (stride >= warp_pairs) {  // crosses the warps' ranges
-          __syncthreads();
-          for (unsigned pr = threadIdx.x; pr < (padded >> 1); pr += kGroupSortThreads) exchange(pr, span, stride);
-          __syncthreads();
-          block_wide = true;
-        } else {
-          (void)block_wide;
-          for (unsigned pr = lane; pr < warp_pairs; pr += 32) exchange(warp * warp_pairs + pr, span, stride);
-          __syncwarp();
-          block_wide = false;
-        }
-      }
-    }
-    __syncthreads();
-    for (unsigned e = threadIdx.x; e < size; e += kGroupSortThreads) {
-      comp_out[first + e] = k[e];
-      idx_out[first + e] = v[e];
-    }
-    __syncthreads();  // the staging area is refilled by the next group
+    const unsigned t = threadIdx.x;
+    if (size <= 2u * kT)
+      sort_one_group<CompT, IdxT, 2, kT>(first, size, t, comp_in, idx_in, comp_out, idx_out, sk, sv);
+    else if (size <= 4u * kT)
+      sort_one_group<CompT, IdxT, 4, kT>(first, size, t, comp_in, idx_in, comp_out, idx_out, sk, sv);
+    else if (size <= 8u * kT)
+      sort_one_group<CompT, IdxT, 8, kT>(first, size, t, comp_in, idx_in, comp_out, idx_out, sk, sv);
+    else
+      sort_one_group<CompT, IdxT, 16, kT>(first, size, t, comp_in, idx_in, comp_out, idx_out, sk, sv);
   }
 }
 
-// Mid groups of at most kWarpGroup suffixes — the bulk of them: a repeat family's 20-mer with one
-// substitution is shared by ~100 copies — are sorted by one warp each (eight groups per CTA at a
-// time, warp barriers only); the CTA-wide kernel above spends most of its threads and all of its
-// block barriers idling on groups this small.
-constexpr unsigned kWarpGroup = 128;
-
+// kSmallGroup < size <= kWarpGroup — the bulk of the mid groups: a repeat family's 20-mer with one
+// substitution is shared by ~100 copies — one warp per group, eight groups per CTA at a time, no
+// shared memory and no barriers at all.
 template <class CompT, class IdxT>
 __global__ void __launch_bounds__(kGroupSortThreads) group_sort_warp_kernel(const IdxT* __restrict__ group_first,
                                                                             const IdxT* __restrict__ group_size,
@@ -835,45 +923,19 @@ __global__ void __launch_bounds__(kGroupSortThreads) group_sort_warp_kernel(cons
                                                                             CompT* __restrict__ comp_out,
                                                                             IdxT* __restrict__ idx_out) {
   constexpr int kWarps = kGroupSortThreads / 32;
-  __shared__ CompT k_all[kWarps][kWarpGroup];
-  __shared__ IdxT v_all[kWarps][kWarpGroup];
+  static_assert(kWarpGroup == 8u * 32u, "the largest warp-sorted group fills eight registers per lane");
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  CompT* k = k_all[warp];
-  IdxT* v = v_all[warp];
   const unsigned long long groups = *group_count;
   for (unsigned long long grp = static_cast<unsigned long long>(blockIdx.x) * kWarps + warp; grp < groups;
        grp += static_cast<unsigned long long>(gridDim.x) * kWarps) {
     const uint64_t first = group_first[grp];
     const unsigned size = static_cast<unsigned>(group_size[grp]);
-    const unsigned padded = size > 64 ? 128u : 64u;
-    for (unsigned e = lane; e < padded; e += 32) {
-      // padding sorts last: largest key and a suffix index no suffix has
-      k[e] = e < size ? comp_in[first + e] : ~CompT(0);
-      v[e] = e < size ? idx_in[first + e] : ~IdxT(0);
-    }
-    __syncwarp();
-    for (unsigned span = 2; span <= padded; span <<= 1) {
-      for (unsigned stride = span >> 1; stride > 0; stride >>= 1) {
-        for (unsigned pr = lane; pr < (padded >> 1); pr += 32) {
-          const unsigned i = ((pr & ~(stride - 1u)) << 1) | (pr & (stride - 1u));
-          const unsigned j = i | stride;
-          const bool up = (i & span) == 0;
-          const CompT a = k[i], b = k[j];
-          const IdxT va = v[i], vb = v[j];
-          const bool greater = a > b || (a == b && va > vb);  // (comp, suffix) pairs are distinct
-          if (greater == up) {
-            k[i] = b, k[j] = a;
-            v[i] = vb, v[j] = va;
-          }
-        }
-        __syncwarp();
-      }
-    }
-    for (unsigned e = lane; e < size; e += 32) {
-      comp_out[first + e] = k[e];
-      idx_out[first + e] = v[e];
-    }
-    __syncwarp();  // the staging area is refilled by the next group
+    if (size <= 64u)
+      sort_one_group<CompT, IdxT, 2, 32>(first, size, lane, comp_in, idx_in, comp_out, idx_out, nullptr, nullptr);
+    else if (size <= 128u)
+      sort_one_group<CompT, IdxT, 4, 32>(first, size, lane, comp_in, idx_in, comp_out, idx_out, nullptr, nullptr);
+    else
+      sort_one_group<CompT, IdxT, 8, 32>(first, size, lane, comp_in, idx_in, comp_out, idx_out, nullptr, nullptr);
   }
 }
 
@@ -935,6 +997,12 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
     IdxT* wf = warp_first.get();
     IdxT* ws = warp_size.get();
     unsigned long long* mc = mid_count.get();
+    static const unsigned warp_limit_env = [] {  // tuning knob: groups up to here go to the warp kernel
+      const char* e = std::getenv("CAPSB_WARP_GROUP");
+      const long v = e ? std::atol(e) : static_cast<long>(kWarpGroup);
+      return static_cast<unsigned>(v < static_cast<long>(kSmallGroup) ? kSmallGroup : v > static_cast<long>(kWarpGroup) ? kWarpGroup : v);
+    }();
+    const unsigned warp_limit = warp_limit_env;
     launch_map(dev, st, m, [=] __device__(uint64_t t) {
       const IdxT grp = g[t];
       // the members of a group are consecutive in the list, in SA order
@@ -954,7 +1022,7 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
             else
               hi = mid;
           }
-          const bool by_warp = hi - first <= kWarpGroup;
+          const bool by_warp = hi - first <= warp_limit;
           const unsigned long long slot = atomicAdd(mc + (by_warp ? 1 : 0), 1ull);
           (by_warp ? wf : mf)[slot] = static_cast<IdxT>(first);
           (by_warp ? ws : ms)[slot] = static_cast<IdxT>(hi - first);
