@@ -377,6 +377,19 @@ struct OpMax {
   __host__ __device__ static T apply(T a, T b) { return a > b ? a : b; }
 };
 
+// Two scans in one over 64-bit values: running maximum of the high halves, sum of the low halves
+// (a sum that stays below 2^32).
+struct OpMaxHiSumLo {
+  template <class T>
+  __host__ __device__ static T identity() { return T(0); }
+  template <class T>
+  __host__ __device__ static T apply(T a, T b) {
+    static_assert(sizeof(T) == 8, "two 32-bit fields");
+    const T ha = a >> 32, hb = b >> 32;
+    return ((ha > hb ? ha : hb) << 32) | static_cast<uint32_t>(a + b);
+  }
+};
+
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;

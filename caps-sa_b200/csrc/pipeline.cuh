@@ -553,10 +553,14 @@ template <class IdxT>
 __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uint64_t* __restrict__ keys,
                                                                        const IdxT* __restrict__ sa,
                                                                        IdxT* __restrict__ lcp,
-                                                                       uint32_t* __restrict__ tied_bits, uint64_t count,
+                                                                       uint32_t* __restrict__ tied_bits,
+                                                                       uint32_t* __restrict__ head_bits, uint64_t count,
                                                                        uint64_t skip, uint64_t chunk, uint64_t n,
-                                                                       unsigned log2_bits, IdxT* __restrict__ partial) {
+                                                                       unsigned log2_bits, IdxT* __restrict__ partial,
+                                                                       uint64_t* __restrict__ head_partial) {
   __shared__ unsigned warp_sums[kKeyLcpThreads / 32];
+  __shared__ uint64_t warp_heads[kKeyLcpThreads / 32];
+  uint64_t last_head = 0;  // 1 + the last position of this chunk that starts a key group (0: none)
   const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;  // a multiple of 128
   const uint64_t end = begin + chunk < count ? begin + chunk : count;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -593,7 +597,7 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
       prev_sa = k0 > 0 ? sa[kp] : IdxT(0);
       next_key = k0 + 4 < count ? keys[k0 + 4] : ~key[3];
     }
-    unsigned nib = 0;
+    unsigned nib = 0, head_nib = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint64_t pk = j ? key[j - 1] : prev_key;
@@ -605,6 +609,7 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
       const bool eq_next = (nk == key[j]) & (k0 + j + 1 < count);
       l[j] = eq_prev ? kLcpUnset<IdxT> : key_lcp_value<IdxT>(pk, key[j], ps, s[j], n, log2_bits);
       nib |= (exists & (eq_prev | eq_next)) ? 1u << j : 0u;
+      head_nib |= (exists & !eq_prev & eq_next) ? 1u << j : 0u;
     }
     if (whole_row) {
       store4(lcp + k0, l);
@@ -620,16 +625,127 @@ __global__ void __launch_bounds__(kKeyLcpThreads) key_lcp_count_kernel(const uin
     word |= __shfl_xor_sync(0xffffffffu, word, 2);
     word |= __shfl_xor_sync(0xffffffffu, word, 4);
     if ((lane & 7u) == 0 && k0 < end) tied_bits[k0 >> 5] = word;
+    // the same for the positions that start a key group of two or more
+    if (head_nib) last_head = k0 + (32u - static_cast<unsigned>(__clz(head_nib)));  // (rows come in increasing order)
+    unsigned head_word = head_nib << (4u * (lane & 7u));
+    head_word |= __shfl_xor_sync(0xffffffffu, head_word, 1);
+    head_word |= __shfl_xor_sync(0xffffffffu, head_word, 2);
+    head_word |= __shfl_xor_sync(0xffffffffu, head_word, 4);
+    if ((lane & 7u) == 0 && k0 < end) head_bits[k0 >> 5] = head_word;
   }
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) tied_here += __shfl_xor_sync(0xffffffffu, tied_here, d);
-  if (lane == 0) warp_sums[warp] = tied_here;
+  for (int d = 16; d > 0; d >>= 1) {
+    tied_here += __shfl_xor_sync(0xffffffffu, tied_here, d);
+    const uint64_t other = __shfl_xor_sync(0xffffffffu, last_head, d);
+    last_head = other > last_head ? other : last_head;
+  }
+  if (lane == 0) warp_sums[warp] = tied_here, warp_heads[warp] = last_head;
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint64_t total = 0;
+    uint64_t total = 0, head = 0;
 #pragma unroll
-    for (int w = 0; w < kKeyLcpThreads / 32; ++w) total += warp_sums[w];
+    for (int w = 0; w < kKeyLcpThreads / 32; ++w) {
+      total += warp_sums[w];
+      head = warp_heads[w] > head ? warp_heads[w] : head;
+    }
     partial[blockIdx.x] = static_cast<IdxT>(total);
+    head_partial[blockIdx.x] = head;
+  }
+}
+
+// Second half of the first pass: the tied positions (bits of tied_bits) leave for the active list
+// — position, suffix, and the head of their key group (the last bit of head_bits at or before
+// them) — one bitmap word (32 positions) per lane and step (a compaction over all n positions, one
+// flag each, and a running-maximum scan over the tied ones took 10 ms at 3.1 Gbp).  slot_base /
+// head_base: per chunk, the exclusive scans (sum / max) of what key_lcp_count_kernel left in
+// partial / head_partial.  Positions count from the aligned start (see `skip` above).
+template <class IdxT>
+__global__ void __launch_bounds__(kScanThreads) tied_collect_kernel(const uint32_t* __restrict__ tied_bits,
+                                                                    const uint32_t* __restrict__ head_bits,
+                                                                    const IdxT* __restrict__ sa, uint64_t count,
+                                                                    uint64_t skip, uint64_t chunk, uint64_t pos_base,
+                                                                    const IdxT* __restrict__ slot_base,
+                                                                    const uint64_t* __restrict__ head_base,
+                                                                    IdxT* __restrict__ pos_a, IdxT* __restrict__ pos_b,
+                                                                    IdxT* __restrict__ idx, IdxT* __restrict__ group) {
+  constexpr int kWarps = kScanThreads / 32;
+  __shared__ unsigned warp_cnt[kWarps];
+  __shared__ uint64_t warp_head[kWarps];
+  __shared__ uint16_t step_rel[kScanThreads * 32];  // tied positions of one step (one word per thread), relative to its first
+  __shared__ uint32_t step_heads[kScanThreads];     // the step's words of head_bits
+  __shared__ uint64_t step_before[kScanThreads];    // 1 + the last group start before each word
+  const uint64_t begin = static_cast<uint64_t>(blockIdx.x) * chunk;  // a multiple of 128
+  const uint64_t end = begin + chunk < count ? begin + chunk : count;
+  const uint64_t w_begin = begin >> 5, w_end = (end + 31) >> 5;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint64_t carry_slot = slot_base[blockIdx.x];
+  uint64_t carry_head = head_base[blockIdx.x];  // 1 + position of the last group start before this chunk (0: none)
+  for (uint64_t wt = w_begin; wt < w_end; wt += kScanThreads) {
+    const uint64_t w = wt + threadIdx.x;
+    const uint32_t tied = w < w_end ? tied_bits[w] : 0u;
+    const uint32_t heads = w < w_end ? head_bits[w] : 0u;
+    const unsigned cnt = __popc(tied);
+    unsigned inc = cnt;
+    uint64_t hmax = heads ? w * 32u + (32u - static_cast<unsigned>(__clz(heads))) : 0ull;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned oc = __shfl_up_sync(0xffffffffu, inc, d);
+      const uint64_t oh = __shfl_up_sync(0xffffffffu, hmax, d);
+      if (lane >= static_cast<unsigned>(d)) {
+        inc += oc;
+        hmax = oh > hmax ? oh : hmax;
+      }
+    }
+    if (lane == 31) warp_cnt[warp] = inc, warp_head[warp] = hmax;
+    __syncthreads();
+    unsigned cnt_before = 0, cnt_total = 0;
+    uint64_t head_before = 0, head_total = 0;
+#pragma unroll
+    for (int v = 0; v < kWarps; ++v) {
+      const unsigned c = warp_cnt[v];
+      const uint64_t h = warp_head[v];
+      if (static_cast<unsigned>(v) < warp) {
+        cnt_before += c;
+        head_before = h > head_before ? h : head_before;
+      }
+      cnt_total += c;
+      head_total = h > head_total ? h : head_total;
+    }
+    uint64_t my_head = __shfl_up_sync(0xffffffffu, hmax, 1);         // last group start before this lane's word
+    if (lane == 0) my_head = 0;
+    my_head = my_head > head_before ? my_head : head_before;
+    my_head = my_head > carry_head ? my_head : carry_head;
+    // Every lane lists the set bits of its word in shared memory, at the slots they will have in
+    // this step's output; then the step's output is written slot by slot, coalesced.  (Measured at
+    // 3.1 Gbp, one position in ten tied: the warp taking its words one after the other, lane b for
+    // bit b, 5.5 ms; every lane storing its own bits straight to global memory, 9.6 ms.)
+    {
+      unsigned at = cnt_before + (inc - cnt);  // slot within this step of the word's first tied position
+      uint32_t bits = tied;
+      while (bits) {
+        const unsigned b = static_cast<unsigned>(__ffs(static_cast<int>(bits))) - 1u;
+        bits &= bits - 1u;
+        step_rel[at++] = static_cast<uint16_t>(threadIdx.x * 32u + b);
+      }
+      step_heads[threadIdx.x] = heads;
+      step_before[threadIdx.x] = my_head;
+    }
+    __syncthreads();
+    for (unsigned j = threadIdx.x; j < cnt_total; j += kScanThreads) {
+      const unsigned rel = step_rel[j], wl = rel >> 5, b = rel & 31u;
+      const uint64_t word_first = (wt + wl) * 32u;
+      const uint64_t k = word_first + b;
+      const uint32_t upto = step_heads[wl] & (0xffffffffu >> (31u - b));
+      // (a tied position always has a group start at or before it: step_before >= 1 when upto == 0)
+      const uint64_t head = upto ? word_first + (31u - static_cast<unsigned>(__clz(upto))) : step_before[wl] - 1;
+      const uint64_t slot = carry_slot + j;
+      pos_a[slot] = pos_b[slot] = static_cast<IdxT>(k - skip);
+      idx[slot] = sa[k];
+      group[slot] = static_cast<IdxT>(pos_base + head - skip);
+    }
+    carry_slot += cnt_total;
+    carry_head = head_total > carry_head ? head_total : carry_head;
+    __syncthreads();  // the warp totals and the step's lists are rewritten by the next step
   }
 }
 
@@ -792,20 +908,27 @@ __device__ __forceinline__ T shfl_xor_words(T x, unsigned lane_mask) {
 
 // (comp, suffix) pairs are distinct except for the padding, whose copies are interchangeable.
 template <class CompT, class IdxT>
+__device__ __forceinline__ bool pair_greater(CompT a, IdxT va, CompT b, IdxT vb) {
+  return (a > b) | ((a == b) & (va > vb));
+}
+
+// Selects, not branches: which way an exchange goes differs from lane to lane.
+template <class CompT, class IdxT>
 __device__ __forceinline__ void compare_exchange(CompT& a, IdxT& va, CompT& b, IdxT& vb, bool up) {
-  const bool greater = a > b || (a == b && va > vb);
-  if (greater == up) {
-    const CompT ta = a;
-    a = b, b = ta;
-    const IdxT tv = va;
-    va = vb, vb = tv;
-  }
+  const bool greater = pair_greater(a, va, b, vb);
+  const bool swap = greater == up;
+  const CompT lo = swap ? b : a, hi = swap ? a : b;
+  const IdxT vlo = swap ? vb : va, vhi = swap ? va : vb;
+  a = lo, b = hi;
+  va = vlo, vb = vhi;
 }
 
 template <class CompT, class IdxT>
 __device__ __forceinline__ void keep_one(CompT& k, IdxT& v, CompT other_k, IdxT other_v, bool keep_min) {
-  const bool mine_greater = k > other_k || (k == other_k && v > other_v);
-  if (mine_greater == keep_min) k = other_k, v = other_v;
+  const bool mine_greater = pair_greater(k, v, other_k, other_v);
+  const bool take = mine_greater == keep_min;
+  k = take ? other_k : k;
+  v = take ? other_v : v;
 }
 
 // Sorts kE * kT pairs ascending: thread t of the kT cooperating ones (a warp: kT == 32, or the
@@ -971,7 +1094,7 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   const DeviceInfo& dev = eng.dev;
   const uint64_t m = act.m;
   DevBuf<CompT> comp_b(m, st);
-  DevBuf<IdxT> idx_b(m, st), head_slot(m, st);
+  DevBuf<IdxT> idx_b(m, st);
 
   // Order every group by the second field.  Groups of at most kSmallGroup suffixes — after the
   // first rounds nearly all of them — are ranked by counting inside the group (one pass, no
@@ -1116,73 +1239,128 @@ void refine_round(Engine& eng, ActiveList<IdxT>& act, IdxT* d_sa, uint64_t pos_b
   const IdxT* sorted_idx = sorted_i;
   trace_point(eng, "  round: large groups sorted");
 
-  IdxT* hs = head_slot.get();
   const IdxT* old_group = act.group.get();
-  scan_full<IdxT, OpMax, true>(
-      eng, m,
-      [=] __device__(uint64_t t) -> IdxT {
-        // a new group starts where the comp changes or the old group does (comps without a group
-        // field can agree across a boundary)
-        return (t > 0 && (sorted_comp[t] != sorted_comp[t - 1] || old_group[t] != old_group[t - 1])) ? static_cast<IdxT>(t)
-                                                                                                  : IdxT(0);
-      },
-      [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
-
-  DevBuf<IdxT> new_group(m, st);
-  {
-    const IdxT* p = act.pos.get();
-    IdxT* ng = new_group.get();
-    launch_map(dev, st, m, [=] __device__(uint64_t t) {
-      const IdxT here = sorted_idx[t];
-      d_sa[p[t]] = here;
-      ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
-      // (captured outside the constexpr-if: an extended lambda may not first-capture inside one)
-      const TextRoundLcp<IdxT> tl = text_lcp;
-      const IdxT* og = old_group;
-      const CompT* sc = sorted_comp;
-      if constexpr (!kGroupInComp && sizeof(CompT) == 8) {
-        if (tl.d_lcp != nullptr && t > 0 && og[t] == og[t - 1]) {
-          const uint64_t ca = static_cast<uint64_t>(sc[t - 1]), cb = static_cast<uint64_t>(sc[t]);
-          if (ca != cb) {
-            uint64_t l;
-            if ((ca & cb) >> 63) {  // both suffixes reach the depth: compare the 63 text bits
-              const uint64_t x = (ca ^ cb) << 1;
-              l = tl.depth + (static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> tl.log2_bits);
-            } else {  // one of them ends before the depth: it is a prefix of its neighbour
-              const uint64_t a = sorted_idx[t - 1], b = here;
-              l = tl.n - (a > b ? a : b);
-            }
-            tl.d_lcp[p[t]] = static_cast<IdxT>(l);
+  const IdxT* p = act.pos.get();
+  DevBuf<IdxT> n_pos, n_idx, n_group;
+  uint64_t m_next = 0;
+  // The LCP a text round settles between position t - 1 and t of the sorted list (see above).
+  auto settle_lcp = [=] __device__(uint64_t t, IdxT here) {
+    // (captured outside the constexpr-if: an extended lambda may not first-capture inside one)
+    const TextRoundLcp<IdxT> tl = text_lcp;
+    const IdxT* og = old_group;
+    const CompT* sc = sorted_comp;
+    const IdxT* si = sorted_idx;
+    const IdxT* pp = p;
+    if constexpr (!kGroupInComp && sizeof(CompT) == 8) {
+      if (tl.d_lcp != nullptr && t > 0 && og[t] == og[t - 1]) {
+        const uint64_t ca = static_cast<uint64_t>(sc[t - 1]), cb = static_cast<uint64_t>(sc[t]);
+        if (ca != cb) {
+          uint64_t l;
+          if ((ca & cb) >> 63) {  // both suffixes reach the depth: compare the 63 text bits
+            const uint64_t x = (ca ^ cb) << 1;
+            l = tl.depth + (static_cast<uint64_t>(__clzll(static_cast<long long>(x))) >> tl.log2_bits);
+          } else {  // one of them ends before the depth: it is a prefix of its neighbour
+            const uint64_t a = si[t - 1], b = here;
+            l = tl.n - (a > b ? a : b);
           }
+          tl.d_lcp[pp[t]] = static_cast<IdxT>(l);
         }
       }
-      (void)tl, (void)og, (void)sc;
-    });
-  }
-  trace_point(eng, "  round: heads + sa written");
-  if (publish_to) {
-    publish_to->publish(sorted_idx, new_group.get(), m);
-    trace_point(eng, "  round: ranks published");
-  }
-
-  auto still_tied = [=] __device__(uint64_t t) -> IdxT {
-    const IdxT h0 = hs[t], h1 = hs[t + 1 < m ? t + 1 : t];  // unconditional loads
-    const bool single = (h0 == t) & ((t + 1 == m) | (h1 == t + 1));
-    return single ? IdxT(0) : IdxT(1);
+    }
+    (void)t, (void)here, (void)tl, (void)og, (void)sc, (void)si, (void)pp;
   };
-  const uint64_t m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
-  DevBuf<IdxT> n_pos(m_next, st), n_idx(m_next, st), n_group(m_next, st);
-  if (m_next > 0) {
-    const IdxT* p = act.pos.get();
-    const IdxT* ng = new_group.get();
+  if constexpr (sizeof(IdxT) == 4) {
+    // One scan does it all (32-bit indices: the list index of a group's first member and the count of
+    // the suffixes that stay tied share a 64-bit value): the first pass counts, so that the new
+    // list can be allocated; the second writes the order, the LCPs, the new group heads and the new list.
+    // A new group starts where the comp changes or the old group does (comps without a group field
+    // can agree across a boundary); a suffix leaves the list when it is alone in its new group.
+    // (all loads unconditional, on clamped indices: a short-circuit would chain their latencies)
+    auto starts = [=] __device__(uint64_t t) -> bool {
+      const uint64_t tp = t > 0 ? t - 1 : 0;
+      return (t == 0) | (sorted_comp[t] != sorted_comp[tp]) | (old_group[t] != old_group[tp]);
+    };
+    auto head_and_tied = [=] __device__(uint64_t t) -> uint64_t {
+      const uint64_t tn = t + 1 < m ? t + 1 : t;
+      const bool s0 = starts(t), s1 = starts(tn) | (t + 1 == m);
+      return ((s0 ? t : 0ull) << 32) | ((s0 & s1) ? 0u : 1u);
+    };
+    m_next = static_cast<uint32_t>(scan_total<uint64_t, OpMaxHiSumLo>(eng, m, head_and_tied));
+    n_pos.alloc(m_next, st), n_idx.alloc(m_next, st), n_group.alloc(m_next, st);
+    DevBuf<IdxT> new_group(publish_to ? m : 0, st);
+    IdxT* ng = publish_to ? new_group.get() : nullptr;
     IdxT* np = n_pos.get();
     IdxT* ns = n_idx.get();
     IdxT* ngp = n_group.get();
-    select_finish<IdxT>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
-      np[slot] = p[t];
-      ns[slot] = sorted_idx[t];
-      ngp[slot] = ng[t];
+    scan_finish<uint64_t, OpMaxHiSumLo, true>(eng, m, head_and_tied, [=] __device__(uint64_t t, uint64_t v) {
+      const uint64_t head = v >> 32;  // list index of the first member of t's new group
+      const IdxT here = sorted_idx[t];
+      const IdxT at = p[t];
+      const IdxT group_head = static_cast<IdxT>(pos_base + p[head]);
+      d_sa[at] = here;
+      if (ng) ng[t] = group_head;
+      settle_lcp(t, here);
+      const uint64_t tn = t + 1 < m ? t + 1 : t;
+      const bool alone = (head == t) & (starts(tn) | (t + 1 == m));
+      if (!alone) {
+        const uint32_t slot = static_cast<uint32_t>(v) - 1u;  // inclusive count of the tied, this one included
+        np[slot] = at;
+        ns[slot] = here;
+        ngp[slot] = group_head;
+      }
     });
+    trace_point(eng, "  round: heads + sa + new list written");
+    if (publish_to) {
+      publish_to->publish(sorted_idx, new_group.get(), m);
+      trace_point(eng, "  round: ranks published");
+    }
+  } else {
+    DevBuf<IdxT> head_slot(m, st);
+    IdxT* hs = head_slot.get();
+    scan_full<IdxT, OpMax, true>(
+        eng, m,
+        [=] __device__(uint64_t t) -> IdxT {
+          // a new group starts where the comp changes or the old group does (comps without a group
+          // field can agree across a boundary)
+          return (t > 0 && (sorted_comp[t] != sorted_comp[t - 1] || old_group[t] != old_group[t - 1])) ? static_cast<IdxT>(t)
+                                                                                                    : IdxT(0);
+        },
+        [=] __device__(uint64_t t, IdxT head) { hs[t] = head; });
+
+    DevBuf<IdxT> new_group(m, st);
+    {
+      IdxT* ng = new_group.get();
+      launch_map(dev, st, m, [=] __device__(uint64_t t) {
+        const IdxT here = sorted_idx[t];
+        d_sa[p[t]] = here;
+        ng[t] = static_cast<IdxT>(pos_base + p[hs[t]]);
+        settle_lcp(t, here);
+      });
+    }
+    trace_point(eng, "  round: heads + sa written");
+    if (publish_to) {
+      publish_to->publish(sorted_idx, new_group.get(), m);
+      trace_point(eng, "  round: ranks published");
+    }
+
+    auto still_tied = [=] __device__(uint64_t t) -> IdxT {
+      const IdxT h0 = hs[t], h1 = hs[t + 1 < m ? t + 1 : t];  // unconditional loads
+      const bool single = (h0 == t) & ((t + 1 == m) | (h1 == t + 1));
+      return single ? IdxT(0) : IdxT(1);
+    };
+    m_next = scan_total<IdxT, OpSum>(eng, m, still_tied);
+    n_pos.alloc(m_next, st), n_idx.alloc(m_next, st), n_group.alloc(m_next, st);
+    if (m_next > 0) {
+      const IdxT* ng = new_group.get();
+      IdxT* np = n_pos.get();
+      IdxT* ns = n_idx.get();
+      IdxT* ngp = n_group.get();
+      select_finish<IdxT>(eng, m, still_tied, [=] __device__(uint64_t t, IdxT slot) {
+        np[slot] = p[t];
+        ns[slot] = sorted_idx[t];
+        ngp[slot] = ng[t];
+      });
+    }
   }
   act.pos = std::move(n_pos);
   act.idx = std::move(n_idx);
@@ -1244,7 +1422,6 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
     return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
   };
   ActiveList<IdxT>& act = state.act;
-  DevBuf<uint32_t> tied_bits;
   // The streaming pass wants 16-byte aligned arrays.  A range that starts in the middle of larger
   // arrays (sa_build.cu: one range of positions at a time) is reached by stepping back `skip` < 4
   // positions — entries of the range before it, which the pass reads but neither counts nor writes.
@@ -1253,18 +1430,37 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
       skip <= pos_base &&
       ((reinterpret_cast<uintptr_t>(keys - skip) | reinterpret_cast<uintptr_t>(d_sa - skip) |
         reinterpret_cast<uintptr_t>(d_lcp - skip)) & 15u) == 0;
+  auto alloc_lists = [&] {
+    act.pos.alloc(act.m, st);
+    act.idx.alloc(act.m, st);
+    act.group.alloc(act.m, st);
+    tied.m = act.m;
+    tied.pos.alloc(act.m, st);
+  };
   if (vector_ok) {
-    // one streaming sweep: key-derived LCPs, tied bitmap, tied count per chunk (key_lcp_count_kernel)
+    // one streaming sweep: key-derived LCPs, bitmaps of the tied positions and of the group starts,
+    // their count / last group start per chunk (key_lcp_count_kernel); then the lists, 32 positions
+    // per lane at a time (tied_collect_kernel)
     ScanScratch<IdxT>& sc = eng.scan_scratch<IdxT>();
     const Chunking ck = make_chunking(count + skip, kScanTile, sc.max_blocks);
-    tied_bits.alloc((count + skip) / 32 + 8, st);
+    const uint64_t words = (count + skip) / 32 + 8;
+    DevBuf<uint32_t> tied_bits(words, st), head_bits(words, st);
+    DevBuf<uint64_t> head_partial(ck.blocks, st);
     CAPSB_LAUNCH((key_lcp_count_kernel<IdxT>), ck.blocks, kKeyLcpThreads, 0, st, keys - skip, d_sa - skip, d_lcp - skip,
-                 tied_bits.get(), count + skip, skip, ck.chunk, n, log2_bits, sc.partial.get());
+                 tied_bits.get(), head_bits.get(), count + skip, skip, ck.chunk, n, log2_bits, sc.partial.get(),
+                 head_partial.get());
     CAPSB_LAUNCH((scan_spine_kernel<IdxT, OpSum>), 1, kScanThreads, 0, st, ck.blocks, sc.partial.get(), sc.total.get());
+    CAPSB_LAUNCH((scan_spine_kernel<uint64_t, OpMax>), 1, kScanThreads, 0, st, ck.blocks, head_partial.get(),
+                 static_cast<uint64_t*>(nullptr));
     IdxT total;
     read_back(st, &total, sc.total.get(), sizeof(IdxT));
     act.m = total;
-  } else {  // arrays that are not 16-byte aligned: the same pass, element by element
+    alloc_lists();
+    if (act.m > 0)
+      CAPSB_LAUNCH((tied_collect_kernel<IdxT>), ck.blocks, kScanThreads, 0, st, tied_bits.get(), head_bits.get(),
+                   d_sa - skip, count + skip, skip, ck.chunk, pos_base, sc.partial.get(), head_partial.get(),
+                   act.pos.get(), tied.pos.get(), act.idx.get(), act.group.get());
+  } else {  // arrays that are not 16-byte aligned: the same, element by element
     auto in_group_and_lcp = [=] __device__(uint64_t k) -> IdxT {
       const uint64_t kp = k > 0 ? k - 1 : 0, kn = k + 1 < count ? k + 1 : k;
       const uint64_t a = keys[kp], b = keys[k], c = keys[kn];
@@ -1275,34 +1471,15 @@ void refine_shallow(Engine& eng, Ranks& ranks, const PackedText& pt, unsigned ke
       return ((kp != k && a == b) | (kn != k && c == b)) ? IdxT(1) : IdxT(0);
     };
     act.m = scan_total<IdxT, OpSum>(eng, count, in_group_and_lcp);
-  }
-  act.pos.alloc(act.m, st);
-  act.idx.alloc(act.m, st);
-  act.group.alloc(act.m, st);
-  tied.m = act.m;
-  tied.pos.alloc(act.m, st);
-  {
+    alloc_lists();
     IdxT* p = act.pos.get();
     IdxT* p0 = tied.pos.get();
     IdxT* s = act.idx.get();
     IdxT* g = act.group.get();
-    auto collect = [=] __device__(uint64_t k, IdxT slot) {
+    select_finish<IdxT>(eng, count, in_group, [=] __device__(uint64_t k, IdxT slot) {
       p[slot] = p0[slot] = static_cast<IdxT>(k);
       s[slot] = d_sa[k];
-    };
-    if (vector_ok) {
-      const uint32_t* bits = tied_bits.get();
-      const IdxT* sa_al = d_sa - skip;
-      select_finish<IdxT>(
-          eng, count + skip, [=] __device__(uint64_t k) -> IdxT { return (bits[k >> 5] >> (k & 31u)) & 1u; },
-          [=] __device__(uint64_t k, IdxT slot) {  // k counts from the aligned start
-            p[slot] = p0[slot] = static_cast<IdxT>(k - skip);
-            s[slot] = sa_al[k];
-          });
-    } else {
-      select_finish<IdxT>(eng, count, in_group, collect);
-    }
-    tied_bits.release();
+    });
     // group head (global SA position) of every active suffix: running maximum of the heads
     scan_full<IdxT, OpMax, true>(
         eng, act.m,
