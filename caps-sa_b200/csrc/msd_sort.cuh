@@ -63,7 +63,7 @@ struct MsdRecordSource {
   unsigned shift, mask;
   __device__ __forceinline__ unsigned digit_of(uint64_t rec) const { return static_cast<unsigned>(rec >> shift) & mask; }
   __device__ __forceinline__ void load_tile(uint64_t tile, unsigned valid, unsigned bins, uint64_t (&rec)[kMsdItems],
-                                            unsigned (&d)[kMsdItems]) const {
+                                            unsigned (&d)[kMsdItems], bool /*counting_only*/ = false) const {
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {  // striped: consecutive threads read consecutive records
       const unsigned e = static_cast<unsigned>(t) * kMsdThreads + threadIdx.x;
@@ -96,6 +96,19 @@ __device__ __forceinline__ void msd_roll_windows(const uint64_t (&w)[4], unsigne
   }
 }
 
+// The same when the key bits of all kMsdItems windows lie inside the first one (key_bits +
+// (kMsdItems - 1) symbols <= 64: DNA with its 40-bit key): window t is window 0 shifted left by t
+// symbols — garbage-free in its key bits, two packed words instead of four, one shift per window.
+template <int kLog2Bits>
+__device__ __forceinline__ void msd_shift_windows(uint64_t cur0, uint64_t (&win)[kMsdItems]) {
+#pragma unroll
+  for (int t = 0; t < kMsdItems; ++t) {
+    constexpr unsigned kShiftCap = 63u;
+    const unsigned sh = static_cast<unsigned>(t) << kLog2Bits;
+    win[t] = cur0 << (sh < kShiftCap ? sh : kShiftCap);  // (sh < 64 whenever the caller's condition holds)
+  }
+}
+
 template <class First, class = void>
 struct MsdIsSequentialText : std::false_type {};
 template <class First>
@@ -109,6 +122,7 @@ struct MsdFirstSource {
   First first;
   unsigned key_shift;  // 64 - key_bits
   unsigned rem_bits;   // key_bits - a
+  unsigned short_windows = 3;  // bit 0: the counting pass, bit 1: the scatter pass may take msd_shift_windows
   __device__ __forceinline__ unsigned digit_of(uint64_t) const { return 0; }  // not recoverable: kDigitInRec = false
   __device__ __forceinline__ void split(uint64_t key, uint64_t suffix, uint64_t& rec, unsigned& d) const {
     const uint64_t k = key >> key_shift;
@@ -116,7 +130,7 @@ struct MsdFirstSource {
     rec = ((k & ((1ull << rem_bits) - 1ull)) << 32) | suffix;
   }
   __device__ __forceinline__ void load_tile(uint64_t tile, unsigned valid, unsigned bins, uint64_t (&rec)[kMsdItems],
-                                            unsigned (&d)[kMsdItems]) const {
+                                            unsigned (&d)[kMsdItems], bool counting_only = false) const {
     if constexpr (MsdIsSequentialText<First>::value) {
       // Consecutive suffixes of the text: the thread takes kMsdItems consecutive ones, loads the
       // (at most four) packed words they span ONCE and shifts every window out of them — one
@@ -128,16 +142,31 @@ struct MsdFirstSource {
       const uint64_t bit0 = p0 << pt.log2_bits;
       const uint64_t w0 = bit0 >> 6;
       const uint64_t nwords = (((pt.n << pt.log2_bits) + 63) >> 6) + 2;
-      uint64_t w[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) w[q] = (e0 < valid && w0 + q < nwords) ? __ldg(pt.words + w0 + q) : 0ull;
       const unsigned o0 = static_cast<unsigned>(bit0 & 63u);
       uint64_t win[kMsdItems];
-      switch (pt.log2_bits) {  // constant shifts per symbol width
-        case 0: msd_roll_windows<0>(w, o0, win); break;
-        case 1: msd_roll_windows<1>(w, o0, win); break;
-        case 2: msd_roll_windows<2>(w, o0, win); break;
-        default: msd_roll_windows<3>(w, o0, win); break;
+      const bool key_bits_in_first_window =
+          ((static_cast<unsigned>(kMsdItems) - 1u) << pt.log2_bits) <= key_shift && ((short_windows >> (counting_only ? 0 : 1)) & 1u);
+      if (key_bits_in_first_window) {  // (uniform over the grid)
+        uint64_t w[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) w[q] = (e0 < valid && w0 + q < nwords) ? __ldg(pt.words + w0 + q) : 0ull;
+        const uint64_t cur0 = o0 ? (w[0] << o0) | (w[1] >> (64u - o0)) : w[0];
+        switch (pt.log2_bits) {  // constant shifts per symbol width
+          case 0: msd_shift_windows<0>(cur0, win); break;
+          case 1: msd_shift_windows<1>(cur0, win); break;
+          case 2: msd_shift_windows<2>(cur0, win); break;
+          default: msd_shift_windows<3>(cur0, win); break;
+        }
+      } else {
+        uint64_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) w[q] = (e0 < valid && w0 + q < nwords) ? __ldg(pt.words + w0 + q) : 0ull;
+        switch (pt.log2_bits) {  // constant shifts per symbol width
+          case 0: msd_roll_windows<0>(w, o0, win); break;
+          case 1: msd_roll_windows<1>(w, o0, win); break;
+          case 2: msd_roll_windows<2>(w, o0, win); break;
+          default: msd_roll_windows<3>(w, o0, win); break;
+        }
       }
 #pragma unroll
       for (int t = 0; t < kMsdItems; ++t) {
@@ -257,7 +286,7 @@ __global__ void __launch_bounds__(kMsdThreads) msd_hist_kernel(Src src, const Ms
     const unsigned valid = static_cast<unsigned>(pc.end - tile < kMsdTile ? pc.end - tile : kMsdTile);
     uint64_t rec[kMsdItems];
     unsigned d[kMsdItems];
-    src.load_tile(tile, valid, bins, rec, d);
+    src.load_tile(tile, valid, bins, rec, d, true);
     const bool aggregate = msd_probe(d[0], d[0] != bins);
 #pragma unroll
     for (int t = 0; t < kMsdItems; ++t) {

@@ -216,8 +216,13 @@ void msd_partition(Engine& eng, FirstSrc first, uint64_t count, unsigned key_bit
   {
     DevBuf<uint64_t> rec_a(count, st);
     // level A: digit = top a bits of the key, records = (remaining bits << 32) | suffix
+    // CAPSB_MSD_SHORT: which level-A passes may shift all of a thread's windows out of the first one
+    // (bit 0 the counting pass, bit 1 the scatter pass; default both)
+    unsigned short_windows = 3;
+    if (const char* env = std::getenv("CAPSB_MSD_SHORT")) short_windows = static_cast<unsigned>(std::atoi(env)) & 3u;
     msd_partition_level<MsdFirstSource<FirstSrc>, false>(
-        dev, st, eng.msd_timers, eng.msd_timers.scatter_a, MsdFirstSource<FirstSrc>{first, 64u - key_bits, rem_a},
+        dev, st, eng.msd_timers, eng.msd_timers.scatter_a,
+        MsdFirstSource<FirstSrc>{first, 64u - key_bits, rem_a, short_windows},
         count, root.get(), 1, a, 2, 4, FirstSrc::bytes_read_per_item(), start_a.get(), rec_a.get());
     // level B: every level-A bucket by the next b bits
     msd_partition_level<MsdRecordSource, true>(dev, st, eng.msd_timers, eng.msd_timers.scatter_b,
