@@ -109,6 +109,31 @@ def genome_like(n: int, seed: int = 3, scale: float | None = None) -> np.ndarray
     return text
 
 
+def repeat_groups(n: int, sizes=(40, 100, 200, 300, 700, 1500, 3000, 5000), block: int = 64, seed: int = 7,
+                  mutated=(2000, 100, 0.05)) -> np.ndarray:
+    """Random ACGT with, for every k in `sizes`, k exact copies of a random block of `block` symbols
+    dropped at random places, plus `mutated = (copies, length, rate)`: copies of one block with
+    substitutions.  Every suffix that starts inside a copy ties with its k - 1 siblings on the rest of
+    the block and differs right after it: tied groups of (about) every listed size, which is what
+    picks the code path of the refinement's group sorts (a warp up to 256, a CTA up to 4096, the
+    global sort above) and of the local sort's ordering loop."""
+    rng = np.random.default_rng([seed, 0xB10C])
+    text = _ACGT[rng.integers(0, 4, size=n, dtype=np.uint8)]
+    for k in sizes:
+        unit = _ACGT[rng.integers(0, 4, size=block, dtype=np.uint8)]
+        for at in rng.integers(0, n - block, size=k):
+            text[at:at + block] = unit
+    copies, length, rate = mutated
+    if copies and length < n:
+        unit = _ACGT[rng.integers(0, 4, size=length, dtype=np.uint8)]
+        for at in rng.integers(0, n - length, size=copies):
+            seg = unit.copy()
+            hit = rng.random(length) < rate
+            seg[hit] = _ACGT[rng.integers(0, 4, size=int(hit.sum()), dtype=np.uint8)]
+            text[at:at + length] = seg
+    return text
+
+
 def ecoli_like_fasta(seed: int = 1, bases: int = 4_641_652) -> np.ndarray:
     """Config 1 stand-in (data/ecoli.fa is absent from the reference mount): a FASTA-shaped
     file — one header line, 80-column lines — with a few injected repeats.  Returned as raw

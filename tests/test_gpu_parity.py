@@ -201,6 +201,8 @@ CASES = {
     "fibonacci_400k": lambda s: (s.fibonacci(400_000), 16),
     "allA_100k": lambda s: (np.full(100_000, ord("A"), dtype=np.uint8), 8),
     "ecoli_like_cli_mapped": lambda s: (s.map_acgt(s.ecoli_like_fasta(seed=1, bases=1_000_000)), 64),
+    # tied groups of 40 .. 5000 suffixes: every size class of the group sorts and of the local sort's ordering loop
+    "repeat_groups_3M": lambda s: (s.repeat_groups(3_000_000), 64),
 }
 
 

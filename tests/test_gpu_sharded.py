@@ -24,6 +24,7 @@ CASES = {
     "period3_100k": lambda s: s.periodic(100_000, b"ACG"),
     "fibonacci_200k": lambda s: s.fibonacci(200_000),
     "allA_50k": lambda s: np.full(50_000, ord("A"), dtype=np.uint8),
+    "repeat_groups_1500k": lambda s: s.repeat_groups(1_500_000),  # tied groups of 40 .. 5000 suffixes
 }
 
 
