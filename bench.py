@@ -83,7 +83,8 @@ NCU_TRAFFIC = {
     "scatter": (NCU_TRAFFIC_RATIO, "profiles/r01/scatter_ncu_full_v4.csv"),
     "msd_scatter_a": ((0.798767e9 + 29.127431e9) / (9.0 * 3.1e9), _S14),
     "msd_scatter_b": ((25.027414e9 + 24.795954e9) / (16.0 * 3.1e9), _S14),
-    "msd_local": ((23.623950e9 + 35.203882e9 + 1.299756e9 + 1.885538e9) / (20.0 * 3.1e9), _S14),
+    "msd_local": ((23.619910e9 + 35.203110e9 + 1.300618e9 + 1.885808e9) / (20.0 * 3.1e9),
+                  "profiles/r02/ncu_full_final_kernels_s24_summary.csv"),
 }
 
 
