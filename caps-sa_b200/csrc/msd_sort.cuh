@@ -599,7 +599,7 @@ template <int kN, int kT, class Smem>
 __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict__ recs,
                                                  uint32_t* __restrict__ sa_out, uint32_t q, uint32_t beg, uint32_t count,
                                                  unsigned rem_bits, unsigned key_shift, unsigned extra_bits,
-                                                 unsigned small_group) {
+                                                 unsigned small_group, uint32_t next_beg, uint32_t next_count) {
   const unsigned tid = threadIdx.x;
   // The first counting pass takes the top hb of the remaining bits: about one counter per record
   // (extra_bits = 1; per two records with 0 — the scan of the counters is per-bucket overhead, the
@@ -618,6 +618,15 @@ __device__ __forceinline__ void msd_local_bucket(Smem& sm, uint64_t* __restrict_
   for (int t = 0; t < kN; ++t) {
     const unsigned e = static_cast<unsigned>(t) * kT + tid;
     rec[t] = e < count ? ld_stream_u64(recs + beg + e) : 0ull;
+  }
+  // While this bucket is ordered, the records of the CTA's next one travel to L2 (one 128-byte line
+  // per thread: no registers held, unlike loading them ahead): the loads above are what the kernel
+  // waits on longest after its barriers (long-scoreboard stalls, profiles/r02 s24).
+  if (next_count > 0) {
+    const uintptr_t first_line = reinterpret_cast<uintptr_t>(recs + next_beg) & ~static_cast<uintptr_t>(127);
+    const uintptr_t end = reinterpret_cast<uintptr_t>(recs + next_beg + next_count);
+    const uintptr_t line = first_line + static_cast<uintptr_t>(tid) * 128u;
+    if (line < end) asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
   }
   if (hb > 0 && count > 1) {
     msd_local_pass<kN, kT>(sm, rec, 0, count, 32u + lb, hb);
@@ -702,7 +711,8 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
                                                                  const uint32_t* __restrict__ bucket_list,
                                                                  uint32_t q_begin, uint32_t q_end, unsigned key_bits,
                                                                  unsigned prefix_bits, unsigned extra_bits,
-                                                                 unsigned small_group, uint32_t* __restrict__ sa_out,
+                                                                 unsigned small_group, bool l2_prefetch,
+                                                                 uint32_t* __restrict__ sa_out,
                                                                  uint32_t* __restrict__ large_list,
                                                                  uint32_t* __restrict__ large_count) {
   extern __shared__ __align__(16) unsigned char msd_smem_raw[];
@@ -719,15 +729,24 @@ __global__ void __launch_bounds__(kT, kMinCtas) msd_local_kernel(uint64_t* __res
     const uint32_t q = bucket_list ? bucket_list[at] : at;
     const uint32_t beg = child_start[q];
     const uint32_t count = child_start[q + 1] - beg;
+    uint32_t next_beg = 0, next_count = 0;  // the bucket this CTA takes after this one (for the L2 prefetch)
+    if (l2_prefetch && at + gridDim.x < q_end) {
+      const uint32_t nq = bucket_list ? bucket_list[at + gridDim.x] : at + gridDim.x;
+      next_beg = child_start[nq];
+      next_count = child_start[nq + 1] - next_beg;
+      if (next_count > static_cast<uint32_t>(kT * kMsdItems)) next_count = 0;  // (not this kernel's: it only lists it)
+    }
     if (count == 0) continue;
     if (count > static_cast<uint32_t>(kT * kMsdItems)) {
       if (tid == 0) large_list[atomicAdd(large_count, 1u)] = q;
       continue;
     }
     if (count <= static_cast<uint32_t>(kHalf * kT))
-      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group);
+      msd_local_bucket<kHalf, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group, next_beg,
+                                  next_count);
     else
-      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group);
+      msd_local_bucket<kMsdItems, kT>(sm, recs, sa_out, q, beg, count, rem_bits, key_shift, extra_bits, small_group,
+                                      next_beg, next_count);
   }
 }
 

@@ -261,6 +261,8 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     const long v = env ? std::atol(env) : static_cast<long>(dflt);
     return static_cast<unsigned>(v < static_cast<long>(kMsdSmallGroup) ? kMsdSmallGroup : v > 2048 ? 2048 : v);
   };
+  // CAPSB_MSD_L2_PREFETCH=0: no prefetch hint for the bucket a CTA takes next
+  const bool l2_prefetch = !(std::getenv("CAPSB_MSD_L2_PREFETCH") && std::getenv("CAPSB_MSD_L2_PREFETCH")[0] == '0');
   const unsigned small_group = group_limit("CAPSB_MSD_SMALL_GROUP", 128);
   const unsigned small_group_big = group_limit("CAPSB_MSD_SMALL_GROUP_BIG", 256);
   {
@@ -270,7 +272,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     MsdTimed timed(eng.msd_timers.local, st, records * (2 * sizeof(uint64_t) + sizeof(uint32_t)));
     CAPSB_LAUNCH((msd_local_kernel<kMsdThreads, CAPSB_MSD_MIN_CTAS>), grid, kMsdThreads, sizeof(Small), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(nullptr), q_begin, q_end, ms.key_bits, ms.a + ms.b,
-                 extra_bits, small_group, sa_out, ms.large_list.get(), counts);
+                 extra_bits, small_group, l2_prefetch, sa_out, ms.large_list.get(), counts);
   }
   uint32_t nlarge = 0;
   read_back(st, &nlarge, counts, sizeof(uint32_t));
@@ -282,7 +284,7 @@ inline void msd_local_sort(Engine& eng, MsdSorted& ms, uint64_t* keys_out, uint3
     MsdTimed timed(eng.msd_timers.local, st, 0);  // (its records are counted with the first launch)
     CAPSB_LAUNCH((msd_local_kernel<kMsdBigThreads, 1>), grid, kMsdBigThreads, sizeof(Big), st, keys_out,
                  ms.start_b.get(), static_cast<const uint32_t*>(ms.large_list.get()), 0u, nlarge, ms.key_bits,
-                 ms.a + ms.b, extra_bits, small_group_big, sa_out, huge_list, counts + 1);
+                 ms.a + ms.b, extra_bits, small_group_big, l2_prefetch, sa_out, huge_list, counts + 1);
   }
   uint32_t nhuge = 0;
   read_back(st, &nhuge, counts + 1, sizeof(uint32_t));
