@@ -12,9 +12,11 @@
 //   level B   every level-A bucket is partitioned by the next `b` bits: 2^(a+b) buckets of a few
 //             thousand records each (a + b is chosen from the number of suffixes);
 //   local     one CTA per bucket: the bucket is loaded into shared memory, ordered by the
-//             remaining bits (one counting pass on their top bits, then each small group is ordered
-//             by comparison, larger groups by one more counting pass), and leaves as the sorted
-//             keys — written in place of the records — plus the suffix array.
+//             remaining bits (one counting pass on their top bits, then each group of up to a
+//             hundred-odd records is ordered by comparison, larger groups by one more counting
+//             pass), and leaves as the sorted keys — written in place of the records — plus the
+//             suffix array.  Two instantiations: 512 threads, two CTAs per SM, for buckets of up
+//             to 6144 records; 1024 threads, one CTA per SM, for those up to 12 288.
 // Three trips through HBM instead of five, 16 B per record and trip instead of 24.  A partition
 // need not be stable (whatever order equal digits come in, the next level sorts them), so a
 // record's rank inside its tile is ONE shared-memory atomicAdd on a per-CTA counter instead of

@@ -1,15 +1,20 @@
 // Building blocks shared by the single-GPU construction (sa_build.cu) and the sharded one
 // (sharded_build.cu):
-//   sort_suffix_slice   stable LSD radix sort of a slice of suffixes on their packed-prefix key
-//                       (replaces permute + sort_subarrays/merge_sort, reference
-//                       src/Suffix_Array.cpp:112-184);
-//   refine_tied_groups  refinement restricted to the suffixes that are still tied — pair chains,
+//   sort_suffixes_by_key / sort_suffix_slice
+//                       key sort of suffixes on their packed-prefix key: the packed-record MSD sort
+//                       of msd_sort.cuh (msd_partition + msd_local_sort) for 32-bit indices, stable
+//                       LSD passes otherwise (replaces permute + sort_subarrays/merge_sort,
+//                       reference src/Suffix_Array.cpp:112-184);
+//   refine_shallow / refine_deep / fix_group_edges (refine_tied_groups = the three in sequence)
+//                       refinement restricted to the suffixes that are still tied — pair chains,
 //                       text rounds, then prefix doubling on ranks (replaces the character
 //                       compares inside merge, :69-80);
 //                       where the ranks live is a policy: one array (LocalRanks) or sharded by
 //                       text position with an exchange per round (ShardedRanks);
-//   key_lcp_count_kernel  first pass over the sorted keys: LCP of neighbours with different keys
-//                       (clz(key_a ^ key_b)), bitmap and counts of the tied positions;
+//   key_lcp_count_kernel, tied_collect_kernel
+//                       first pass over the sorted keys: LCP of neighbours with different keys
+//                       (clz(key_a ^ key_b)), bitmaps of the tied positions and of the starts of
+//                       their key groups; the lists of the tied positions from the bitmaps;
 //   plcp_for_pairs      LCP of tied neighbours by the permuted-LCP recurrence
 //                       PLCP[i] = PLCP[i-1] - 1 on reducible positions and a packed-word
 //                       comparison on the irreducible ones (replaces the LCPs carried
@@ -531,12 +536,13 @@ constexpr IdxT kLcpUnset = ~IdxT(0);
 // ---------------------------------------------------------------------------------------
 // First pass over the key-sorted suffixes (one streaming sweep, 128-bit accesses, four
 // consecutive positions per thread): writes the LCP of every position whose key differs from
-// its predecessor's (clz of the key XOR), marks the others unset, records in a bitmap which
-// positions sit in a key group of two or more (= still tied) and counts them per chunk, with
-// the chunking of the compaction that follows (select_finish), which then reads one bit per
-// position instead of the keys again.  Algorithmic traffic: 8 + w read, w written per suffix.
+// its predecessor's (clz of the key XOR), marks the others unset, records in one bitmap which
+// positions sit in a key group of two or more (= still tied) and in another which of them start
+// their group, and leaves per chunk the count of the tied and (1 +) the last group start —
+// what tied_collect_kernel needs to turn the bitmaps into lists without reading the keys again.
+// Algorithmic traffic: 8 + w read, w written per suffix.
 // Entries next to a tied group are provisional (their bound depends on which member ends up at
-// the group's edge); refine_tied_groups rewrites them at the end.
+// the group's edge); fix_group_edges rewrites them at the end.
 // ---------------------------------------------------------------------------------------
 constexpr int kKeyLcpThreads = 256;
 

@@ -1,15 +1,20 @@
 // Suffix-array + LCP construction on one B200 (the hot path).
 //
 // Replaces the reference's construct() pipeline (src/Suffix_Array.cpp:466-494):
-//   permute + sort_subarrays/merge_sort/merge (:112-184)  ->  one stable LSD radix sort of all
-//       suffixes on their 64-bit packed-prefix key (radix_sort.cuh), keys read straight
-//       from the packed text;
-//   character-compare tie resolution inside merge (:69-80)  ->  prefix-doubling rank
-//       refinement restricted to the suffixes that are still tied ("discarding");
+//   permute + sort_subarrays/merge_sort/merge (:112-184)  ->  a key sort of all suffixes on the top
+//       key_bits of their packed text: most significant digit first on packed 8-byte records
+//       (msd_sort.cuh: two partition levels read straight from the packed text, then one CTA per
+//       bucket in shared memory); stable LSD passes (radix_sort.cuh) for 64-bit indices;
+//   character-compare tie resolution inside merge (:69-80)  ->  refinement restricted to the
+//       suffixes that are still tied: pair chains, text rounds, then prefix doubling on ranks
+//       (pipeline.cuh: refine_shallow / refine_deep / fix_group_edges);
 //   LCP carried through merges (:61-68,:78)  ->  clz(key_a ^ key_b) for neighbours with
-//       different keys; for tied neighbours the permuted-LCP recurrence
-//       PLCP[i] = PLCP[i-1] - 1 on reducible positions and a direct packed-word
-//       comparison on the irreducible ones (sum of irreducible LCPs <= 2 n log n).
+//       different keys, the common leading symbols of the comps for neighbours a text round
+//       separates; for the rest the permuted-LCP recurrence PLCP[i] = PLCP[i-1] - 1 on
+//       reducible positions and a direct packed-word comparison on the irreducible ones
+//       (sum of irreducible LCPs <= 2 n log n).
+// With result arrays in pinned host memory the construction runs a range of SA positions at a
+// time (plan_ranges) and copies every finished range out while the next one is refined.
 // The output is the canonical SA/LCP under signed-char order, shorter suffix first —
 // bit-identical to the reference at its default (unbounded) context.
 #include <cstdlib>
